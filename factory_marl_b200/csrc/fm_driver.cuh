@@ -1,0 +1,128 @@
+// fm_driver.cuh — phase schedule of one env step for a block of E envs (shared by the CUDA kernel and by the
+// host-compiled logic-test build).  `Run` executes one barrier interval: on the GPU it calls the body for
+// threadIdx.x and then __syncthreads(); in the host test build it loops over all thread ids.
+//
+// Order of one control step (reference: BaseEnv.step_sim base_env.py:240-282):
+//   load state (cubes in their pre-edit pose) -> derive (mj_step1 of the pre-edit state: the reference does not
+//   re-run kinematics after TaskManager writes qpos, so the first sub-step sees stale contacts) -> apply edits ->
+//   100 x { PT1 filter, actuation, smooth acceleration, PGS, implicitfast, integrate, derive } -> force check ->
+//   task logic, reward, observation, optional auto-reset -> store.
+#pragma once
+#include "fm_task.cuh"
+
+struct FmDebugDump {   // optional per-launch dump of one env's intermediates after the first derive (tests only)
+  int env, ncon, nqueue, flags;
+  int c_g[FM_MAXCON];
+  float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_dist[FM_MAXCON], c_f[FM_MAXCON][4];
+  float body_x[FM_MAX_ARMS][FM_NARMBODY][3], body_R[FM_MAX_ARMS][FM_NARMBODY][9];
+  float M[FM_MAX_ARMS][45], bias[FM_MAX_ARMS][9];
+  float acc_smooth[61 + 9 * FM_MAX_ARMS], acc[61 + 9 * FM_MAX_ARMS];
+  int pgs_iters;
+};
+
+struct FmStepArgs {
+  const float* act_f; const int* act_i;
+  float* obs; float* reward; unsigned char* terminated; int* scores; unsigned char* flags; float* terminal_obs; float* ep_info;
+  const unsigned char* reset_mask;
+  int auto_reset;
+  int mode;          // 0 = env step, 1 = reset only (mask or all), 2 = raw sub-steps (debug: no action map / task logic)
+  int n_substeps;    // mode 2
+  FmDebugDump* dump;
+};
+
+template <int NA, int E, class Run>
+FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned short* cpairs, const int* geom_class, int T) {
+  run([&](int tid) { ph_clear<NA, E>(S, tid, T); ph_cube_derive<NA, E>(S, tid, T); ph_arm_fk<NA, E>(S, m, tid, T, true); });
+  run([&](int tid) { ph_arm_body<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_arm_backward<NA, E>(S, m, tid, T); ph_broad<NA, E>(S, m, cpairs, tid, T); });
+  run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); ph_narrow<NA, E>(S, m, cpairs, tid, T); });
+  run([&](int tid) { ph_arm_chol<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_arm_minv<NA, E>(S, tid, T); });
+  run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T); ph_arm_rows<NA, E>(S, m, tid, T); });
+}
+
+template <int NA, int E>
+FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
+  if (!d || tid != 0) return;
+  int e = d->env - env0;
+  if (e < 0 || e >= E) return;
+  const EnvS<NA>& s = S[e];
+  if (stage == 0) {
+    d->ncon = s.ncon; d->nqueue = s.nqueue; d->flags = s.flags;
+    for (int c = 0; c < s.ncon && c < FM_MAXCON; ++c) {
+      d->c_g[c] = s.c_g[c];
+      for (int k = 0; k < 3; ++k) { d->c_p[c][k] = s.c_p[c][k]; d->c_n[c][k] = s.c_n[c][k]; }
+    }
+    for (int a = 0; a < NA; ++a) {
+      for (int b = 0; b < FM_NARMBODY; ++b) { for (int k = 0; k < 3; ++k) d->body_x[a][b][k] = s.body_x[a][b][k]; for (int k = 0; k < 9; ++k) d->body_R[a][b][k] = s.body_R[a][b][k]; }
+      for (int k = 0; k < 45; ++k) d->M[a][k] = s.M[a][k];
+      for (int k = 0; k < 9; ++k) d->bias[a][k] = s.bias[a][k];
+    }
+  } else if (stage == 1) {
+    for (int k = 0; k < EnvS<NA>::NV; ++k) d->acc_smooth[k] = s.acc[k];
+  } else {
+    for (int k = 0; k < EnvS<NA>::NV; ++k) d->acc[k] = s.acc[k];
+    for (int c = 0; c < s.ncon && c < FM_MAXCON; ++c) for (int r = 0; r < 4; ++r) d->c_f[c][r] = s.c_f[c][r];
+  }
+}
+
+template <int NA, int E, class Run>
+FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const unsigned short* cpairs, const int* geom_class,
+                         const FmEnvCfg& cfg, const FmStatePtrs& st, const FmStepArgs& ar, int env0) {
+  const int T = 32 * E;
+  typedef Lay<NA> L;
+  const int obs_dim = L::obs_dim(cfg.env_class);
+  run([&](int tid) { ph_load<NA, E>(S, TS, st, env0, tid, T); });
+  if (ar.mode == 1) {   // reset only: masked envs (or all) go to the initial state, the others are written back untouched
+    run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
+    run([&](int tid) {
+      for (int w = tid; w < E; w += T) {
+        int env = env0 + w;
+        if (env >= st.n) continue;
+        bool doit = ar.reset_mask ? ar.reset_mask[env] != 0 : true;
+        TS[w].done_prev = doit; TS[w].terminated = doit;
+        if (doit) task_reset_state(S[w], TS[w], cfg);
+      }
+    });
+    run([&](int tid) { ph_arm_fk<NA, E>(S, m, tid, T, false); });
+    run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, tid, T, true); });
+    run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
+    return;
+  }
+  if (ar.mode == 0) run([&](int tid) { ph_action<NA, E>(S, TS, m, cfg, st, ar.act_f, ar.act_i, env0, tid, T); });
+  else run([&](int tid) {   // debug: ctrl_target is used as is (no filter): ctrl := ctrl_target
+    for (int w = tid; w < EnvS<NA>::NU * E; w += T) S[w % E].ctrl[w / E] = S[w % E].ctrl_target[w / E];
+  });
+  fm_derive<NA, E>(run, S, m, cpairs, geom_class, T);
+  run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
+  const double hd = cfg.dt / cfg.frame_skip;
+  const float alpha = (float)(hd / (hd + cfg.pt_time));   // base_env.py:209-211
+  const int nsub = ar.mode == 0 ? cfg.frame_skip : ar.n_substeps;
+  for (int t = 0; t < nsub; ++t) {
+    if (t > 0) fm_derive<NA, E>(run, S, m, cpairs, geom_class, T);
+    run([&](int tid) { ph_islands<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, alpha); });
+    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
+    run([&](int tid) { ph_smooth<NA, E>(S, m, tid, T); });
+    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 1); });
+    for (int o = 0; o < cfg.pgs_outer; ++o) {
+      run([&](int tid) { ph_pgs<NA, E>(S, m, tid, T, o == 0, cfg.pgs_inner, cfg.pgs_tol); });
+      run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); });
+    }
+    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 2); });
+    run([&](int tid) { if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });
+  }
+  if (ar.mode == 2) {   // debug: store the raw state, pre-edit == current
+    run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, tid, T); for (int w = tid; w < E; w += T) TS[w].done_prev = 0; });
+    run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
+    return;
+  }
+  // kinematics of the final state for the gripper sites (reward / IK policy read site_xpos after the last mj_step1)
+  run([&](int tid) { ph_arm_fk<NA, E>(S, m, tid, T, false); ph_store_pre<NA, E>(S, st, env0, tid, T); });
+  run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); });
+  run([&](int tid) { ph_task<NA, E>(S, TS, m, cfg, st, env0, tid, T); });
+  run([&](int tid) { ph_obs<NA, E>(S, TS, ar.terminal_obs, obs_dim, st.n, env0, tid, T, true); ph_outputs<NA, E>(S, TS, st, ar.reward, ar.terminated, ar.scores, ar.flags, ar.ep_info, env0, tid, T); });
+  if (ar.auto_reset) run([&](int tid) { ph_reset_done<NA, E>(S, TS, cfg, st, env0, tid, T, nullptr); });
+  else run([&](int tid) { for (int w = tid; w < E; w += T) TS[w].done_prev = 0; });
+  run([&](int tid) { ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, tid, T, false); });
+  run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
+}

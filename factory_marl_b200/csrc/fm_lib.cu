@@ -1,0 +1,173 @@
+// fm_lib.cu — CUDA kernels (sm_100a) + the C-ABI of include/fm_api.h.
+// Kernels:
+//   fm_step_kernel<NA,E>   fused env step: 100 x mj_step-equivalent + task logic for E envs per CTA (fm_driver.cuh)
+//   fm_ik_kernel<NA>       IK base policy + FSM, fp64, thread per env (fm_ik.cuh)
+// No CPU fallback: every entry point launches CUDA work or fails with an error.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <new>
+#include "fm_host_common.h"
+#include "fm_ik.cuh"
+
+static thread_local std::string g_err;
+#define FM_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return 2; } } while (0)
+
+struct DevRun {
+  template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); __syncthreads(); }
+};
+
+template <int NA, int E>
+__global__ void __launch_bounds__(32 * E) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned short* __restrict__ cpairs,
+                                                         const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EnvS<NA>* S = reinterpret_cast<EnvS<NA>*>(smem_raw);
+  TaskS* TS = reinterpret_cast<TaskS*>(S + E);
+  // zero the block's shared state (counters, lists)
+  {
+    int* z = reinterpret_cast<int*>(smem_raw);
+    const int nw = (int)((E * (sizeof(EnvS<NA>) + sizeof(TaskS))) / 4);
+    for (int i = threadIdx.x; i < nw; i += 32 * E) z[i] = 0;
+    __syncthreads();
+  }
+  DevRun run;
+  fm_block_step<NA, E>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
+}
+
+template <int NA>
+__global__ void fm_ik_kernel(const FmIkModel* __restrict__ ik, FmEnvCfg cfg, FmStatePtrs st, float* obs, int obs_dim) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= st.n) return;
+  fm_ik_env<NA>(*ik, cfg, st, obs, obs_dim, env);
+}
+
+struct fm_handle {
+  FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st;
+  int E = 4; size_t smem = 0;
+  FmDevModel* d_model = nullptr; FmIkModel* d_ik = nullptr; unsigned short* d_cpairs = nullptr; int* d_geom_class = nullptr;
+  FmDebugDump* d_dump = nullptr;
+  long long launches = 0;
+};
+
+template <int NA, int E>
+static int launch_step(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
+  size_t smem = E * (sizeof(EnvS<NA>) + sizeof(TaskS));
+  static bool attr_set = false;
+  if (!attr_set) { FM_CUDA(cudaFuncSetAttribute(fm_step_kernel<NA, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  int nblk = (h->cfg.n_envs + E - 1) / E;
+  fm_step_kernel<NA, E><<<nblk, 32 * E, smem, s>>>(h->d_model, h->d_cpairs, h->d_geom_class, h->cfg, h->st, ar);
+  FM_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
+  if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
+  if (h->hm.n_arms == 2) {
+    if (h->E == 8) return launch_step<2, 8>(h, ar, s);
+    return launch_step<2, 4>(h, ar, s);
+  }
+  return launch_step<4, 4>(h, ar, s);
+}
+
+extern "C" {
+const char* fm_last_error(void) { return g_err.c_str(); }
+
+int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {
+  try {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: this library has no CPU path"; return 3; }
+    fm_handle* h = new fm_handle();
+    fm_build_host_model(blob, n, h->hm);
+    if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
+    if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4 are built");
+    if (cfg->env_class < 0 || cfg->env_class > 6) throw std::runtime_error("bad env_class");
+    h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
+    int E = cfg->envs_per_block;
+    h->E = (h->hm.n_arms == 2 && E == 8) ? 8 : 4;
+    h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs};
+    FM_CUDA(cudaMalloc(&h->d_model, sizeof(FmDevModel)));
+    FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMalloc(&h->d_ik, sizeof(FmIkModel)));
+    FM_CUDA(cudaMemcpy(h->d_ik, &h->hm.ik, sizeof(FmIkModel), cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMalloc(&h->d_cpairs, h->hm.cpairs.size() * sizeof(unsigned short)));
+    FM_CUDA(cudaMemcpy(h->d_cpairs, h->hm.cpairs.data(), h->hm.cpairs.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMalloc(&h->d_geom_class, h->hm.geom_class.size() * sizeof(int)));
+    FM_CUDA(cudaMemcpy(h->d_geom_class, h->hm.geom_class.data(), h->hm.geom_class.size() * sizeof(int), cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMalloc(&h->d_dump, sizeof(FmDebugDump)));
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+int fm_destroy(fm_handle* h) {
+  if (!h) return 0;
+  cudaFree(h->d_model); cudaFree(h->d_ik); cudaFree(h->d_cpairs); cudaFree(h->d_geom_class); cudaFree(h->d_dump);
+  delete h; return 0;
+}
+int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : Lay<4>::obs_dim(h->cfg.env_class); }
+int fm_act_dim(const fm_handle* h) { return fm_act_dim_of(h->cfg.env_class, h->hm.n_arms); }
+int fm_state_rows(const fm_handle* h, int32_t* nf, int32_t* nd, int32_t* ni) {
+  if (h->hm.n_arms == 2) { *nf = Lay<2>::NF; *nd = Lay<2>::ND; *ni = Lay<2>::NI; } else { *nf = Lay<4>::NF; *nd = Lay<4>::ND; *ni = Lay<4>::NI; }
+  return 0;
+}
+int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng) {
+  h->st.f = f; h->st.d = d; h->st.i = i; h->st.rng = (unsigned long long*)rng; return 0;
+}
+int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : fm_field_offset_t<4>(name); }
+long long fm_launch_count(const fm_handle* h) { return h->launches; }
+
+int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream) {
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.reset_mask = mask; ar.obs = obs;
+  return dispatch(h, ar, (cudaStream_t)stream);
+}
+int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores, uint8_t* flags,
+            float* terminal_obs, float* ep_info, void* stream) {
+  if (!actions && fm_act_dim(h) > 0) { g_err = "fm_step: actions is NULL"; return 1; }
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar));
+  ar.mode = 0; ar.act_f = (const float*)actions; ar.act_i = (const int*)actions; ar.obs = obs; ar.reward = reward; ar.terminated = terminated;
+  ar.scores = scores; ar.flags = flags; ar.terminal_obs = terminal_obs; ar.ep_info = ep_info; ar.auto_reset = h->user.auto_reset;
+  return dispatch(h, ar, (cudaStream_t)stream);
+}
+int fm_ik_policy(fm_handle* h, float* obs, void* stream) {
+  if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
+  int N = h->cfg.n_envs, od = fm_obs_dim(h), tpb = 64, nb = (N + tpb - 1) / tpb;
+  if (h->hm.n_arms == 2) fm_ik_kernel<2><<<nb, tpb, 0, (cudaStream_t)stream>>>(h->d_ik, h->cfg, h->st, obs, od);
+  else fm_ik_kernel<4><<<nb, tpb, 0, (cudaStream_t)stream>>>(h->d_ik, h->cfg, h->st, obs, od);
+  FM_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+static int copy_state_to_host(fm_handle* h, std::vector<float>& f, std::vector<int>& iv) {
+  int32_t nf, nd, ni; fm_state_rows(h, &nf, &nd, &ni);
+  f.resize((size_t)nf * h->st.n); iv.resize((size_t)ni * h->st.n);
+  FM_CUDA(cudaDeviceSynchronize());
+  FM_CUDA(cudaMemcpy(f.data(), h->st.f, f.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  FM_CUDA(cudaMemcpy(iv.data(), h->st.i, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int fm_get_state(fm_handle* h, fm_state_view* v) {
+  std::vector<float> f; std::vector<int> iv;
+  if (int rc = copy_state_to_host(h, f, iv)) return rc;
+  if (h->hm.n_arms == 2) fm_view_get<2>(f.data(), h->st.n, v); else fm_view_get<4>(f.data(), h->st.n, v);
+  return 0;
+}
+int fm_set_state(fm_handle* h, const fm_state_view* v) {
+  std::vector<float> f; std::vector<int> iv;
+  if (int rc = copy_state_to_host(h, f, iv)) return rc;
+  if (h->hm.n_arms == 2) { fm_view_set<2>(f.data(), h->st.n, v); fm_view_clear_warm<2>(iv.data(), h->st.n, v->env); }
+  else { fm_view_set<4>(f.data(), h->st.n, v); fm_view_clear_warm<4>(iv.data(), h->st.n, v->env); }
+  FM_CUDA(cudaMemcpy(h->st.f, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FM_CUDA(cudaMemcpy(h->st.i, iv.data(), iv.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void* stream) {
+  FmDebugDump hd; memset(&hd, 0, sizeof(hd)); hd.env = view ? view->env : -1;
+  FM_CUDA(cudaMemcpy(h->d_dump, &hd, sizeof(hd), cudaMemcpyHostToDevice));
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? h->d_dump : nullptr;
+  if (int rc = dispatch(h, ar, (cudaStream_t)stream)) return rc;
+  FM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (view) {
+    FM_CUDA(cudaMemcpy(&hd, h->d_dump, sizeof(hd), cudaMemcpyDeviceToHost));
+    if (h->hm.n_arms == 2) fm_dump_to_view<2>(hd, view); else fm_dump_to_view<4>(hd, view);
+  }
+  return 0;
+}
+}  // extern "C"

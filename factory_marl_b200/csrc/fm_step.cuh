@@ -1,0 +1,928 @@
+// fm_step.cuh — the fused "env step" kernel body: 100 x { mj_step-equivalent } + task logic, one CTA per E envs.
+//
+// Replaces, for the scene of scene.py:109-169, what the reference computes in
+//   BaseEnv._step_sim_unscaled   challenge_env/challenge_env/base_env.py:204-238  (PT1 filter + 100 x physics.step())
+//   physics.step()               base_env.py:218  (MuJoCo mj_step2 + mj_step1, third party)
+// Design (B200): one env's whole state lives in shared memory for the 100 sub-steps (HBM touched once per
+// env-step); the CTA runs a sequence of barrier-separated *phases*, each phase mapping threads to the natural
+// work items of that stage (arm chains, bodies, mass-matrix entries, cluster pairs, contacts, constraint islands),
+// so serial per-arm recursions of all E envs pack into one warp while wide stages use the whole CTA.
+// The constraint problem is solved by projected Gauss-Seidel on the dual in contact space (3x3 Delassus blocks,
+// exact GS inside a constraint island, islands in parallel, belt coupling lagged), warm-started from qacc.
+//
+// Every phase is a plain function of (block, tid) with no intra-phase cross-thread dependency, so the same source
+// also compiles with g++ for host-side logic tests (tests/kernel_emu); the product only ever launches the CUDA build.
+#pragma once
+#include "fm_types.h"
+#include "fm_math.cuh"
+#include "fm_collide.cuh"
+#include <string.h>
+
+#if defined(__CUDA_ARCH__)
+#define FM_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define FM_ATOMIC_ADDF(p, v) atomicAdd((p), (v))
+#define FM_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define FM_ATOMIC_MAXI(p, v) atomicMax((p), (v))
+#else
+template <class T> static inline T fm_host_add(T* p, T v) { T o = *p; *p = o + v; return o; }
+static inline int fm_host_or(int* p, int v) { int o = *p; *p = o | v; return o; }
+static inline int fm_host_max(int* p, int v) { int o = *p; *p = o > v ? o : v; return o; }
+#define FM_ATOMIC_ADD(p, v) fm_host_add((p), (v))
+#define FM_ATOMIC_ADDF(p, v) fm_host_add((p), (v))
+#define FM_ATOMIC_OR(p, v) fm_host_or((p), (v))
+#define FM_ATOMIC_MAXI(p, v) fm_host_max((p), (v))
+#endif
+
+#define FM_QMAX 96
+#define FM_AROW 10   // equality + up to 9 limit rows per arm
+
+// packed lower-triangular index
+FM_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <int NA>
+struct EnvS {
+  static const int NV = 61 + 9 * NA, NQ = 71 + 9 * NA, NU = 1 + 8 * NA, NNODE = FM_NCUBE + NA;
+  // ---- state (persisted in HBM between env steps)
+  float belt_q, belt_v;
+  float cube_q[FM_NCUBE][7], cube_v[FM_NCUBE][6];
+  float arm_q[NA][9], arm_v[NA][9];
+  float ctrl_target[NU], ctrl[NU];
+  float acc_ws[NV];                         // qacc_warmstart: [0] belt, [1+6k] cube k, [61+9a] arm a
+  float conveyor_speed;
+  // ---- position-dependent (mj_step1)
+  float cube_R[FM_NCUBE][9], cube_x[FM_NCUBE][3];
+  float body_x[NA][FM_NARMBODY][3], body_R[NA][FM_NARMBODY][9], cl_x[NA][FM_NARMBODY][3];
+  float M[NA][45], Minv[NA][81], Li[NA][45], Lc[NA][45];
+  float bias[NA][9];
+  // ---- acceleration stage
+  float acc[NV];
+  float belt_acc_smooth, belt_S;
+  // ---- arm-local rows (joint equality gripper.xml:46-49, joint limits)
+  int arow_n[NA], arow_code[NA][FM_AROW];   // code: dof | sign<<8 (sign bit 1 = negative) ; 0x1000 = equality
+  float arow_aref[NA][FM_AROW], arow_R[NA][FM_AROW], arow_f[NA][FM_AROW];
+  // ---- contacts
+  int ncon, nraw, n_armside, flags, nqueue;
+  int raw_key[FM_MAXCON], raw_g[FM_MAXCON];
+  float raw_d[FM_MAXCON][7];
+  int c_side[FM_MAXCON], c_g[FM_MAXCON];
+  float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_mu[FM_MAXCON], c_R[FM_MAXCON], c_W[FM_MAXCON][6];
+  float c_aref[FM_MAXCON][4], c_f[FM_MAXCON][4];
+  float as_J[FM_MAXARMSIDE][27], as_B[FM_MAXARMSIDE][27];
+  int isl_root[NNODE], isl_start[NNODE + 1];
+  unsigned char isl_list[FM_MAXCON];
+  unsigned short queue[FM_QMAX];
+  // ---- per-body scratch of the arm recursions
+  float d_c[NA][FM_NARMBODY][3], d_Ic[NA][FM_NARMBODY][6], d_comp[NA][FM_NARMBODY][10];
+  float d_om[NA][FM_NARMBODY][3], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3];
+  float d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3];
+  float force_max;
+  // forces of the previous solve, keyed by contact identity (warm start of the dual; persisted in HBM between env steps)
+  int prev_n, prev_key[FM_MAXCON];
+  float prev_f[FM_MAXCON][4];
+  int prev_arow_n[NA], prev_arow_code[NA][FM_AROW];
+  float prev_arow_f[NA][FM_AROW];
+  int c_key[FM_MAXCON];
+  int pad_;
+};
+
+// flags
+#define FM_FLAG_CON_OVERFLOW 1
+#define FM_FLAG_ARMSIDE_OVERFLOW 2
+#define FM_FLAG_QUEUE_OVERFLOW 4
+#define FM_FLAG_NAN 8
+
+// side descriptor packing: type (2 bits) | idx (6 bits: cube k or arm*16+body) | slot (4 bits) per side; bit 31 = arm geom involved
+FM_HD int pack_side(int type, int idx, int slot) { return type | (idx << 2) | (slot << 9); }
+FM_HD int side_type(int s) { return s & 3; }
+FM_HD int side_idx(int s) { return (s >> 2) & 127; }
+FM_HD int side_slot(int s) { return (s >> 9) & 15; }
+
+// parent of template body b (0 base .. 10 right plate)
+FM_HD int ab_parent(int b) { return b <= 8 ? b - 1 : 8; }
+// dof index (0..8) of template body b, or -1
+FM_HD int ab_dof(int b) { return (b >= 1 && b <= 7) ? b - 1 : (b == 9 ? 7 : (b == 10 ? 8 : -1)); }
+FM_HD int dof_body(int d) { return d < 7 ? d + 1 : d + 2; }
+
+// =====================================================================================================================
+// phase: cube kinematics (normalise quats in place as mj_kinematics does [3P])
+template <int NA, int E>
+FM_HD void ph_cube_derive(EnvS<NA>* S, int tid, int T) {
+  for (int w = tid; w < FM_NCUBE * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int k = w / E;
+    q4 q = qnormf(mkq(s.cube_q[k][3], s.cube_q[k][4], s.cube_q[k][5], s.cube_q[k][6]));
+    s.cube_q[k][3] = q.w; s.cube_q[k][4] = q.x; s.cube_q[k][5] = q.y; s.cube_q[k][6] = q.z;
+    q2matf(q, s.cube_R[k]);
+    s.cube_x[k][0] = s.cube_q[k][0]; s.cube_x[k][1] = s.cube_q[k][1]; s.cube_x[k][2] = s.cube_q[k][2];
+  }
+}
+
+// phase: arm forward kinematics + Newton-Euler forward recursion (angular velocity, bias accelerations).
+// One thread per (env, arm); world-aligned axes, link-origin reference points.
+template <int NA, int E>
+FM_HD void ph_arm_fk(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool with_vel) {
+  for (int w = tid; w < NA * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int a = w / E;
+    q4 q = mkq(m.arm_base_quat[a][0], m.arm_base_quat[a][1], m.arm_base_quat[a][2], m.arm_base_quat[a][3]);
+    f3 x = ld3(m.arm_base_pos[a]);
+    float Rp[9];
+    q2matf(q, Rp);
+    st3(s.body_x[a][0], x);
+    for (int i = 0; i < 9; ++i) s.body_R[a][0][i] = Rp[i];
+    f3 om = mk3(0, 0, 0), al = mk3(0, 0, 0), ap = mk3(0, 0, m.g);
+    if (with_vel) { st3(s.d_om[a][0], om); st3(s.d_al[a][0], al); st3(s.d_ap[a][0], ap); }
+    // gripper base frame kept for the two plates
+    q4 q8 = q; f3 x8 = x, om8 = om, al8 = al, ap8 = ap; float R8[9];
+    for (int b = 1; b < FM_NARMBODY; ++b) {
+      if (b >= 9) { q = q8; x = x8; om = om8; al = al8; ap = ap8; for (int i = 0; i < 9; ++i) Rp[i] = R8[i]; }
+      f3 r = rmul(Rp, ld3(m.ab_pos[b]));
+      q = qmulf(q, mkq(m.ab_quat[b][0], m.ab_quat[b][1], m.ab_quat[b][2], m.ab_quat[b][3]));
+      int d = ab_dof(b);
+      float R[9];
+      f3 axv = mk3(0, 0, 0);
+      if (m.ab_jtype[b] == 1) {
+        float sn, cs;
+        sincosf(0.5f * s.arm_q[a][d], &sn, &cs);
+        q = qmulf(q, mkq(cs, 0, 0, sn));
+        q = qnormf(q);
+        q2matf(q, R);
+        if (with_vel) axv = rcol(R, 2) * s.arm_v[a][d];
+      } else if (m.ab_jtype[b] == 2) {
+        q = qnormf(q);
+        q2matf(q, R);
+        f3 ax = rcol(R, 0);
+        r = r + ax * s.arm_q[a][d];
+        if (with_vel) axv = ax * s.arm_v[a][d];
+      } else {
+        q = qnormf(q);
+        q2matf(q, R);
+      }
+      if (with_vel) {
+        // acceleration of the new origin (bias part, qacc = 0), then angular quantities
+        ap = ap + cross3(al, r) + cross3(om, cross3(om, r));
+        if (m.ab_jtype[b] == 1) { al = al + cross3(om, axv); om = om + axv; }
+        else if (m.ab_jtype[b] == 2) { ap = ap + 2.0f * cross3(om, axv); }
+        st3(s.d_om[a][b], om); st3(s.d_al[a][b], al); st3(s.d_ap[a][b], ap);
+      }
+      x = x + r;
+      st3(s.body_x[a][b], x);
+      for (int i = 0; i < 9; ++i) { s.body_R[a][b][i] = R[i]; Rp[i] = R[i]; }
+      if (b == 8) { q8 = q; x8 = x; om8 = om; al8 = al; ap8 = ap; for (int i = 0; i < 9; ++i) R8[i] = R[i]; }
+    }
+  }
+}
+
+// phase: per-body quantities (parallel): COM offset, world inertia, composite init, NE body wrench, cluster centre
+template <int NA, int E>
+FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
+    const float* R = s.body_R[a][b];
+    st3(s.cl_x[a][b], ld3(s.body_x[a][b]) + rmul(R, ld3(m.arm_cl[b])));
+    if (b == 0) continue;
+    float ms = m.ab_mass[b];
+    f3 c = rmul(R, ld3(m.ab_ipos[b]));
+    // Iw = R Il R^T
+    const float* Il = m.ab_I[b];
+    float T1[9];   // R * Il
+    for (int i = 0; i < 3; ++i) {
+      float r0 = R[3 * i], r1 = R[3 * i + 1], r2 = R[3 * i + 2];
+      T1[3 * i] = r0 * Il[0] + r1 * Il[3] + r2 * Il[4];
+      T1[3 * i + 1] = r0 * Il[3] + r1 * Il[1] + r2 * Il[5];
+      T1[3 * i + 2] = r0 * Il[4] + r1 * Il[5] + r2 * Il[2];
+    }
+    float Iw[6];
+    Iw[0] = T1[0] * R[0] + T1[1] * R[1] + T1[2] * R[2];
+    Iw[1] = T1[3] * R[3] + T1[4] * R[4] + T1[5] * R[5];
+    Iw[2] = T1[6] * R[6] + T1[7] * R[7] + T1[8] * R[8];
+    Iw[3] = T1[0] * R[3] + T1[1] * R[4] + T1[2] * R[5];
+    Iw[4] = T1[0] * R[6] + T1[1] * R[7] + T1[2] * R[8];
+    Iw[5] = T1[3] * R[6] + T1[4] * R[7] + T1[5] * R[8];
+    st3(s.d_c[a][b], c);
+    for (int i = 0; i < 6; ++i) s.d_Ic[a][b][i] = Iw[i];
+    float cc = dot3(c, c);
+    float* cp = s.d_comp[a][b];
+    cp[0] = ms; cp[1] = ms * c.x; cp[2] = ms * c.y; cp[3] = ms * c.z;
+    cp[4] = Iw[0] + ms * (cc - c.x * c.x); cp[5] = Iw[1] + ms * (cc - c.y * c.y); cp[6] = Iw[2] + ms * (cc - c.z * c.z);
+    cp[7] = Iw[3] - ms * c.x * c.y; cp[8] = Iw[4] - ms * c.x * c.z; cp[9] = Iw[5] - ms * c.y * c.z;
+    // Newton-Euler body wrench about the body origin (bias: qacc = 0, gravity folded into the base acceleration)
+    f3 om = ld3(s.d_om[a][b]), al = ld3(s.d_al[a][b]), ap = ld3(s.d_ap[a][b]);
+    f3 ac = ap + cross3(al, c) + cross3(om, cross3(om, c));
+    f3 f = ac * ms;
+    f3 n = symmul6(Iw, al) + cross3(om, symmul6(Iw, om)) + cross3(c, f);
+    st3(s.d_f[a][b], f); st3(s.d_n[a][b], n);
+  }
+}
+
+// phase: backward recursions (thread per arm): composite inertias about body origins, NE wrench accumulation, bias
+template <int NA, int E>
+FM_HD void ph_arm_backward(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  for (int w = tid; w < NA * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int a = w / E;
+    for (int b = FM_NARMBODY - 1; b >= 2; --b) {
+      int p = ab_parent(b);
+      f3 r = ld3(s.body_x[a][b]) - ld3(s.body_x[a][p]);
+      const float* cc = s.d_comp[a][b]; float* cp = s.d_comp[a][p];
+      float ms = cc[0]; f3 hh = mk3(cc[1], cc[2], cc[3]);
+      float rr = dot3(r, r), rh = dot3(r, hh);
+      float dg = ms * rr + 2.0f * rh;
+      cp[0] += ms; cp[1] += hh.x + ms * r.x; cp[2] += hh.y + ms * r.y; cp[3] += hh.z + ms * r.z;
+      cp[4] += cc[4] + dg - (ms * r.x * r.x + 2.0f * r.x * hh.x);
+      cp[5] += cc[5] + dg - (ms * r.y * r.y + 2.0f * r.y * hh.y);
+      cp[6] += cc[6] + dg - (ms * r.z * r.z + 2.0f * r.z * hh.z);
+      cp[7] += cc[7] - (ms * r.x * r.y + r.x * hh.y + hh.x * r.y);
+      cp[8] += cc[8] - (ms * r.x * r.z + r.x * hh.z + hh.x * r.z);
+      cp[9] += cc[9] - (ms * r.y * r.z + r.y * hh.z + hh.y * r.z);
+      // wrench
+      f3 f = ld3(s.d_f[a][b]), n = ld3(s.d_n[a][b]);
+      st3(s.d_f[a][p], ld3(s.d_f[a][p]) + f);
+      st3(s.d_n[a][p], ld3(s.d_n[a][p]) + n + cross3(r, f));
+    }
+    for (int d = 0; d < 9; ++d) {
+      int b = dof_body(d);
+      const float* R = s.body_R[a][b];
+      s.bias[a][d] = d < 7 ? dot3(rcol(R, 2), ld3(s.d_n[a][b])) : dot3(rcol(R, 0), ld3(s.d_f[a][b]));
+    }
+  }
+}
+
+// phase: mass matrix entries M_ij (parallel over 45 pairs per arm) from composite inertias (CRBA)
+template <int NA, int E>
+FM_HD void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  for (int w = tid; w < NA * 45 * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ap = w / E; int a = ap / 45, pr = ap % 45;
+    int i = 0; while ((i + 1) * (i + 2) / 2 <= pr) ++i;
+    int j = pr - i * (i + 1) / 2;
+    float val = 0.f;
+    if (!(i == 8 && j == 7)) {        // the two plates are siblings: no coupling
+      int bi = dof_body(i), bj = dof_body(j);
+      const float* cp = s.d_comp[a][bi];
+      f3 hh = mk3(cp[1], cp[2], cp[3]);
+      f3 n, f;
+      if (i < 7) { f3 ax = rcol(s.body_R[a][bi], 2); n = symmul6(cp + 4, ax); f = cross3(ax, hh); }
+      else { f3 ax = rcol(s.body_R[a][bi], 0); f = ax * cp[0]; n = cross3(hh, ax); }
+      if (j < 7) {
+        f3 r = ld3(s.body_x[a][bi]) - ld3(s.body_x[a][bj]);
+        val = dot3(rcol(s.body_R[a][bj], 2), n + cross3(r, f));
+      } else {
+        val = dot3(rcol(s.body_R[a][bj], 0), f);
+      }
+    }
+    s.M[a][pr] = val;
+  }
+}
+
+// phase: Cholesky factors (thread per arm): Lc = chol(M), Li = chol(M - h*D) with D = d(actuator force)/d(qvel) [3P implicitfast]
+template <int NA, int E>
+FM_HD void ph_arm_chol(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  for (int w = tid; w < 2 * NA * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ai = w / E; int a = ai >> 1, which = ai & 1;
+    float L[45];
+    for (int i = 0; i < 45; ++i) L[i] = s.M[a][i];
+    if (which) {
+      for (int d = 0; d < 7; ++d) L[tri(d, d)] += m.h * m.kd;
+      float gd = m.h * m.g_kd;   // gripper tendon actuator: moment^T * kd * moment (never force-clamped in range)
+      L[tri(7, 7)] += gd * m.ten0 * m.ten0; L[tri(8, 8)] += gd * m.ten1 * m.ten1; L[tri(8, 7)] += gd * m.ten0 * m.ten1;
+    }
+    for (int i = 0; i < 9; ++i)
+      for (int j = 0; j <= i; ++j) {
+        float sum = L[tri(i, j)];
+        for (int k = 0; k < j; ++k) sum -= L[tri(i, k)] * L[tri(j, k)];
+        if (i == j) L[tri(i, i)] = sqrtf(fmaxf(sum, 1e-20f));
+        else L[tri(i, j)] = sum / L[tri(j, j)];
+      }
+    float* out = which ? s.Li[a] : s.Lc[a];
+    for (int i = 0; i < 45; ++i) out[i] = L[i];
+  }
+}
+
+FM_HD void chol9_solve(const float* L, float* x) {
+  for (int i = 0; i < 9; ++i) { float sum = x[i]; for (int k = 0; k < i; ++k) sum -= L[tri(i, k)] * x[k]; x[i] = sum / L[tri(i, i)]; }
+  for (int i = 8; i >= 0; --i) { float sum = x[i]; for (int k = i + 1; k < 9; ++k) sum -= L[tri(k, i)] * x[k]; x[i] = sum / L[tri(i, i)]; }
+}
+
+// phase: explicit inverse, one column per thread
+template <int NA, int E>
+FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
+  for (int w = tid; w < NA * 9 * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ac = w / E; int a = ac / 9, c = ac % 9;
+    float x[9];
+    for (int i = 0; i < 9; ++i) x[i] = i == c ? 1.f : 0.f;
+    chol9_solve(s.Lc[a], x);
+    for (int i = 0; i < 9; ++i) s.Minv[a][9 * i + c] = x[i];
+  }
+}
+
+// =====================================================================================================================
+// broad phase: one cluster pair per work item; survivors are queued for the narrow phase
+template <int NA>
+FM_HD bool cluster_sphere(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, f3& c, float& r) {
+  if (kind == FM_CL_CUBE) { c = ld3(s.cube_x[idx]); r = m.cube_half[idx] * 1.7320509f; return true; }
+  if (kind == FM_CL_ARM) { int a = idx / FM_NARMBODY, b = idx % FM_NARMBODY; c = ld3(s.cl_x[a][b]); r = m.arm_cl[b][3]; return true; }
+  return false;
+}
+template <int NA>
+FM_HD void cluster_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, f3& p, const float*& R, f3& hs, float* Rid) {
+  if (kind == FM_CL_SBOX) { p = ld3(m.sbox_pos[idx]); R = m.sbox_R[idx]; hs = ld3(m.sbox_half[idx]); }
+  else {  // belt: slides along +y, identity orientation
+    p = mk3(m.belt_pos[0], m.belt_pos[1] + s.belt_q, m.belt_pos[2]); hs = ld3(m.belt_half);
+    Rid[0] = 1; Rid[1] = 0; Rid[2] = 0; Rid[3] = 0; Rid[4] = 1; Rid[5] = 0; Rid[6] = 0; Rid[7] = 0; Rid[8] = 1; R = Rid;
+  }
+}
+
+template <int NA, int E>
+FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned short* __restrict__ cpairs, int tid, int T) {
+  int np = m.n_cluster_pair;
+  for (int w = tid; w < np * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int pi = w / E;
+    int c1 = cpairs[2 * pi], c2 = cpairs[2 * pi + 1];
+    int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2], i1 = m.cl_idx[c1], i2 = m.cl_idx[c2];
+    f3 ca, cb; float ra, rb;
+    bool sa = cluster_sphere(s, m, k1, i1, ca, ra), sb = cluster_sphere(s, m, k2, i2, cb, rb);
+    bool far = false;
+    if (sa && sb) { f3 d = ca - cb; float rr = ra + rb; far = dot3(d, d) > rr * rr; }
+    else if (sa || sb) {
+      f3 c = sa ? ca : cb; float r = sa ? ra : rb; int ko = sa ? k2 : k1, io = sa ? i2 : i1;
+      if (ko == FM_CL_PLANE) far = c.z - r > 0.f;
+      else { f3 p, hs; const float* R; float Rid[9]; cluster_box(s, m, ko, io, p, R, hs, Rid); far = far_sphere_box(c, r, p, R, hs); }
+    }
+    else {   // two big geoms (floor / static box / belt): only the belt moves, along its own long axis
+      if (k1 == FM_CL_PLANE) far = k2 != FM_CL_BELT || m.belt_pos[2] - m.belt_half[2] > 0.f;
+      else if (k2 == FM_CL_BELT) { f3 p, hs; const float* R; float Rid[9]; cluster_box(s, m, k2, i2, p, R, hs, Rid); far = far_sphere_box(ld3(m.sbox_pos[i1]), norm3(ld3(m.sbox_half[i1])), p, R, hs); }
+      else far = true;
+    }
+    if (far) continue;
+    int slot = FM_ATOMIC_ADD(&s.nqueue, 1);
+    if (slot < FM_QMAX) s.queue[slot] = (unsigned short)pi; else FM_ATOMIC_OR(&s.flags, FM_FLAG_QUEUE_OVERFLOW);
+  }
+}
+
+// ---- narrow phase helpers
+template <int NA>
+FM_HD void emit(EnvS<NA>& s, int g1, int g2, int side1, int side2, bool armgeom, const RawC* rc, int n) {
+  if (n <= 0) return;
+  int slot = FM_ATOMIC_ADD(&s.nraw, n);
+  for (int k = 0; k < n; ++k) {
+    int i = slot + k;
+    if (i >= FM_MAXCON) { FM_ATOMIC_OR(&s.flags, FM_FLAG_CON_OVERFLOW); break; }
+    s.raw_key[i] = (g1 << 13) | (g2 << 4) | k;
+    s.raw_g[i] = side1 | (side2 << 13) | (armgeom ? (1 << 30) : 0);
+    s.raw_d[i][0] = rc[k].pos.x; s.raw_d[i][1] = rc[k].pos.y; s.raw_d[i][2] = rc[k].pos.z;
+    s.raw_d[i][3] = rc[k].n.x; s.raw_d[i][4] = rc[k].n.y; s.raw_d[i][5] = rc[k].n.z; s.raw_d[i][6] = rc[k].dist;
+  }
+}
+
+struct GeomBox { f3 p; const float* R; f3 hs; int geom, side, cls; };
+
+template <int NA>
+FM_HD void get_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, int sub, GeomBox& g, float* Rid) {
+  if (kind == FM_CL_SBOX) { g.p = ld3(m.sbox_pos[idx]); g.R = m.sbox_R[idx]; g.hs = ld3(m.sbox_half[idx]); g.geom = m.sbox_geom[idx]; g.side = pack_side(FM_SIDE_STATIC, 0, 0); g.cls = m.sbox_class[idx]; }
+  else if (kind == FM_CL_BELT) { cluster_box(s, m, kind, idx, g.p, g.R, g.hs, Rid); g.geom = m.belt_geom; g.side = pack_side(FM_SIDE_BELT, 0, 0); g.cls = m.belt_class; }
+  else if (kind == FM_CL_CUBE) { g.p = ld3(s.cube_x[idx]); g.R = s.cube_R[idx]; float h = m.cube_half[idx]; g.hs = mk3(h, h, h); g.geom = m.cube_geom[idx]; g.side = pack_side(FM_SIDE_CUBE, idx, 0); g.cls = m.cube_class; }
+  else {  // arm body box `sub`
+    int a = idx / FM_NARMBODY, b = idx % FM_NARMBODY;
+    g.R = s.body_R[a][b]; g.p = ld3(s.body_x[a][b]) + rmul(g.R, ld3(m.abox_pos[sub])); g.hs = ld3(m.abox_half[sub]);
+    g.geom = m.arm_first_geom[a] + m.abox_geom[sub]; g.side = pack_side(FM_SIDE_ARM, a * 16 + b, 0); g.cls = m.abox_class;
+  }
+}
+
+template <int NA>
+FM_HD void pair_box_box(EnvS<NA>& s, const GeomBox& x, const GeomBox& y, bool armgeom) {
+  const GeomBox& g1 = x.geom < y.geom ? x : y; const GeomBox& g2 = x.geom < y.geom ? y : x;
+  if (far_sphere_box(g2.p, norm3(g2.hs), g1.p, g1.R, g1.hs) || far_sphere_box(g1.p, norm3(g1.hs), g2.p, g2.R, g2.hs)) return;
+  RawC rc[8];
+  int n = col_box_box(g1.p, g1.R, g1.hs, g2.p, g2.R, g2.hs, rc);
+  emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rc, n);
+}
+
+template <int NA, int E>
+FM_HD void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned short* __restrict__ cpairs, int tid, int T) {
+  for (int w = tid; w < FM_QMAX * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int qi = w / E;
+    int nq = s.nqueue < FM_QMAX ? s.nqueue : FM_QMAX;
+    if (qi >= nq) continue;
+    int pi = s.queue[qi];
+    int c1 = cpairs[2 * pi], c2 = cpairs[2 * pi + 1];
+    int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2], i1 = m.cl_idx[c1], i2 = m.cl_idx[c2];
+    RawC rc[8]; float RidA[9], RidB[9];
+    if (k2 != FM_CL_ARM) {
+      // no arm involved: plane/sbox/belt/cube vs belt/cube
+      if (k1 == FM_CL_PLANE) {
+        if (k2 == FM_CL_CUBE) { float h = m.cube_half[i2]; int n = col_plane_box(ld3(s.cube_x[i2]), s.cube_R[i2], mk3(h, h, h), rc); emit(s, 0, m.cube_geom[i2], pack_side(FM_SIDE_STATIC, 0, 0), pack_side(FM_SIDE_CUBE, i2, 0), false, rc, n); }
+        else if (k2 == FM_CL_BELT) { GeomBox b; get_box(s, m, k2, i2, 0, b, RidB); int n = col_plane_box(b.p, b.R, b.hs, rc); emit(s, 0, b.geom, pack_side(FM_SIDE_STATIC, 0, 0), b.side, false, rc, n); }
+      } else {
+        GeomBox x, y; get_box(s, m, k1, i1, 0, x, RidA); get_box(s, m, k2, i2, 0, y, RidB);
+        pair_box_box(s, x, y, false);
+      }
+      continue;
+    }
+    // second cluster is an arm body
+    int a2 = i2 / FM_NARMBODY, b2 = i2 % FM_NARMBODY;
+    int s0 = m.body_sph_start[b2], s1 = m.body_sph_start[b2 + 1], x0 = m.body_box_start[b2], x1 = m.body_box_start[b2 + 1];
+    int side2 = b2 == 0 ? pack_side(FM_SIDE_STATIC, 0, 0) : pack_side(FM_SIDE_ARM, a2 * 16 + b2, 0);
+    const float* R2 = s.body_R[a2][b2]; f3 p2 = ld3(s.body_x[a2][b2]);
+    if (k1 == FM_CL_PLANE) {
+      for (int si = s0; si < s1; ++si) { int n = col_plane_sphere(p2 + rmul(R2, ld3(m.sph_pos[si])), m.sph_r[si], rc); emit(s, 0, m.arm_first_geom[a2] + m.sph_geom[si], pack_side(FM_SIDE_STATIC, 0, 0), side2, true, rc, n); }
+      for (int bi = x0; bi < x1; ++bi) { GeomBox g; get_box(s, m, k2, i2, bi, g, RidB); int n = col_plane_box(g.p, g.R, g.hs, rc); emit(s, 0, g.geom, pack_side(FM_SIDE_STATIC, 0, 0), g.side, true, rc, n); }
+    } else if (k1 != FM_CL_ARM) {   // static box / belt / cube  vs  arm body
+      GeomBox x; get_box(s, m, k1, i1, 0, x, RidA);
+      for (int si = s0; si < s1; ++si) {
+        int n = col_sphere_box(p2 + rmul(R2, ld3(m.sph_pos[si])), m.sph_r[si], x.p, x.R, x.hs, rc);
+        emit(s, m.arm_first_geom[a2] + m.sph_geom[si], x.geom, side2, x.side, true, rc, n);     // sphere is geom1 (lower type) [3P]
+      }
+      for (int bi = x0; bi < x1; ++bi) { GeomBox g; get_box(s, m, k2, i2, bi, g, RidB); pair_box_box(s, x, g, true); }
+    } else {                        // arm body vs arm body
+      int a1 = i1 / FM_NARMBODY, b1 = i1 % FM_NARMBODY;
+      int t0 = m.body_sph_start[b1], t1 = m.body_sph_start[b1 + 1], y0 = m.body_box_start[b1], y1 = m.body_box_start[b1 + 1];
+      int side1 = b1 == 0 ? pack_side(FM_SIDE_STATIC, 0, 0) : pack_side(FM_SIDE_ARM, a1 * 16 + b1, 0);
+      const float* R1 = s.body_R[a1][b1]; f3 p1 = ld3(s.body_x[a1][b1]);
+      for (int si = t0; si < t1; ++si) {
+        f3 sp = p1 + rmul(R1, ld3(m.sph_pos[si])); float sr = m.sph_r[si]; int sg = m.arm_first_geom[a1] + m.sph_geom[si];
+        for (int sj = s0; sj < s1; ++sj) {
+          f3 sq = p2 + rmul(R2, ld3(m.sph_pos[sj])); int gj = m.arm_first_geom[a2] + m.sph_geom[sj];
+          if (sg < gj) { int n = col_sphere_sphere(sp, sr, sq, m.sph_r[sj], rc); emit(s, sg, gj, side1, side2, true, rc, n); }
+          else { int n = col_sphere_sphere(sq, m.sph_r[sj], sp, sr, rc); emit(s, gj, sg, side2, side1, true, rc, n); }
+        }
+        for (int bj = x0; bj < x1; ++bj) { GeomBox g; get_box(s, m, k2, i2, bj, g, RidB); int n = col_sphere_box(sp, sr, g.p, g.R, g.hs, rc); emit(s, sg, g.geom, side1, g.side, true, rc, n); }
+      }
+      for (int bi = y0; bi < y1; ++bi) {
+        GeomBox g1; get_box(s, m, k1, i1, bi, g1, RidA);
+        for (int sj = s0; sj < s1; ++sj) { f3 sq = p2 + rmul(R2, ld3(m.sph_pos[sj])); int n = col_sphere_box(sq, m.sph_r[sj], g1.p, g1.R, g1.hs, rc); emit(s, m.arm_first_geom[a2] + m.sph_geom[sj], g1.geom, side2, g1.side, true, rc, n); }
+        for (int bj = x0; bj < x1; ++bj) { GeomBox g2; get_box(s, m, k2, i2, bj, g2, RidB); pair_box_box(s, g1, g2, true); }
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
+// constraint setup
+FM_HD void impedance_f(const float* solref, const float* solimp, float pos, float h, float& K, float& B, float& imp) {
+  float dmin = clampf(solimp[0], 0.0001f, 0.9999f), dmax = clampf(solimp[1], 0.0001f, 0.9999f);
+  float width = fmaxf(solimp[2], 0.f), mid = clampf(solimp[3], 0.0001f, 0.9999f), power = fmaxf(solimp[4], 1.f);
+  if (dmin == dmax || width <= 1e-15f) imp = 0.5f * (dmin + dmax);
+  else {
+    float x = fabsf(pos) / width, y;
+    if (x >= 1.f) y = 1.f;
+    else if (x <= 0.f) y = 0.f;
+    else if (power == 1.f) y = x;
+    else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
+    else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+    imp = dmin + y * (dmax - dmin);
+  }
+  float tc = fmaxf(solref[0], 2.f * h), dr = solref[1];
+  K = 1.f / fmaxf(1e-15f, dmax * dmax * tc * tc * dr * dr);
+  B = 2.f / fmaxf(1e-15f, dmax * tc);
+}
+
+// per-side working set of a contact (contact-space Jacobian base rows n, t1, t2)
+struct SideW {
+  int type, idx;
+  float sgn;
+  f3 ja[3];            // cube: angular rows (body-local)
+  float invm, invI;
+  float jb[3];         // belt: scalar rows
+  const float* J; const float* B;   // arm: 3x9 each
+};
+
+template <int NA>
+FM_HD void side_prepare(const EnvS<NA>& s, const FmDevModel& m, int sd, float sgn, f3 p, f3 n, f3 t1, f3 t2, SideW& o) {
+  o.type = side_type(sd); o.idx = side_idx(sd); o.sgn = sgn;
+  if (o.type == FM_SIDE_CUBE) {
+    int k = o.idx;
+    f3 r = p - ld3(s.cube_x[k]);
+    o.ja[0] = rmulT(s.cube_R[k], cross3(r, n)); o.ja[1] = rmulT(s.cube_R[k], cross3(r, t1)); o.ja[2] = rmulT(s.cube_R[k], cross3(r, t2));
+    o.invm = 1.0f / m.cube_mass[k]; o.invI = 1.0f / m.cube_inertia[k];
+  } else if (o.type == FM_SIDE_BELT) {
+    o.jb[0] = n.y; o.jb[1] = t1.y; o.jb[2] = t2.y;
+  } else if (o.type == FM_SIDE_ARM) {
+    int sl = side_slot(sd);
+    o.J = s.as_J[sl]; o.B = s.as_B[sl];
+  }
+}
+// u += sgn * Jbase * vec  (vec: per-block generalized vector)
+template <int NA>
+FM_HD void side_dot(const SideW& o, f3 n, f3 t1, f3 t2, const float* belt, const float* cube, const float* arm, float* u) {
+  if (o.type == FM_SIDE_CUBE) {
+    const float* v = cube + 6 * o.idx;
+    f3 vl = mk3(v[0], v[1], v[2]), va = mk3(v[3], v[4], v[5]);
+    u[0] += o.sgn * (dot3(n, vl) + dot3(o.ja[0], va)); u[1] += o.sgn * (dot3(t1, vl) + dot3(o.ja[1], va)); u[2] += o.sgn * (dot3(t2, vl) + dot3(o.ja[2], va));
+  } else if (o.type == FM_SIDE_BELT) {
+    float v = belt[0];
+    u[0] += o.sgn * o.jb[0] * v; u[1] += o.sgn * o.jb[1] * v; u[2] += o.sgn * o.jb[2] * v;
+  } else if (o.type == FM_SIDE_ARM) {
+    const float* v = arm + 9 * (o.idx >> 4);
+    for (int d = 0; d < 3; ++d) { float acc = 0.f; for (int k = 0; k < 9; ++k) acc += o.J[9 * d + k] * v[k]; u[d] += o.sgn * acc; }
+  }
+}
+// acc += Minv * Jbase^T * (sgn * lam)
+template <int NA>
+FM_HD void side_apply(const SideW& o, f3 n, f3 t1, f3 t2, float* cube, float* arm, const float* lam) {
+  if (o.type == FM_SIDE_CUBE) {
+    float* v = cube + 6 * o.idx;
+    f3 fl = (n * lam[0] + t1 * lam[1] + t2 * lam[2]) * (o.sgn * o.invm);
+    f3 fa = (o.ja[0] * lam[0] + o.ja[1] * lam[1] + o.ja[2] * lam[2]) * (o.sgn * o.invI);
+    v[0] += fl.x; v[1] += fl.y; v[2] += fl.z; v[3] += fa.x; v[4] += fa.y; v[5] += fa.z;
+  } else if (o.type == FM_SIDE_ARM) {
+    float* v = arm + 9 * (o.idx >> 4);
+    for (int k = 0; k < 9; ++k) v[k] += o.sgn * (o.B[k] * lam[0] + o.B[9 + k] * lam[1] + o.B[18 + k] * lam[2]);
+  }
+}
+
+template <int NA, int E>
+FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T) {
+  for (int w = tid; w < FM_MAXCON * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ri = w / E;
+    int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
+    if (ri >= nraw) continue;
+    int key = s.raw_key[ri];
+    int rank = 0;
+    for (int k = 0; k < nraw; ++k) rank += (s.raw_key[k] < key) ? 1 : 0;
+    int c = rank;
+    int g1 = key >> 13, g2 = (key >> 4) & 511;
+    int rg = s.raw_g[ri];
+    int sd1 = rg & 8191, sd2 = (rg >> 13) & 8191; bool armgeom = (rg >> 30) & 1;
+    f3 p = mk3(s.raw_d[ri][0], s.raw_d[ri][1], s.raw_d[ri][2]), n = mk3(s.raw_d[ri][3], s.raw_d[ri][4], s.raw_d[ri][5]);
+    float dist = s.raw_d[ri][6];
+    f3 t1, t2; make_frame3(n, t1, t2);
+    const float* pp = m.pair_param[geom_class[g1]][geom_class[g2]];
+    float mu = pp[0];
+    // arm sides: Jacobian rows and Minv J^T
+    int sds[2] = {sd1, sd2};
+    float invw = 0.f;
+    for (int sdi = 0; sdi < 2; ++sdi) {
+      int sd = sds[sdi];
+      int ty = side_type(sd), ix = side_idx(sd);
+      if (ty == FM_SIDE_CUBE) invw += m.cube_invw[ix];
+      else if (ty == FM_SIDE_BELT) invw += m.belt_invw;
+      else if (ty == FM_SIDE_ARM) {
+        int a = ix >> 4, b = ix & 15;
+        invw += m.ab_invw[b];
+        int sl = FM_ATOMIC_ADD(&s.n_armside, 1);
+        if (sl >= FM_MAXARMSIDE) { FM_ATOMIC_OR(&s.flags, FM_FLAG_ARMSIDE_OVERFLOW); sds[sdi] = pack_side(FM_SIDE_STATIC, 0, 0); continue; }
+        sds[sdi] = pack_side(ty, ix, sl);
+        float* J = s.as_J[sl]; float* Bv = s.as_B[sl];
+        f3 dirs[3] = {n, t1, t2};
+        for (int d = 0; d < 9; ++d) {
+          int bd = dof_body(d);
+          bool on = d < 7 ? (bd <= b) : (bd == b);
+          f3 colv = mk3(0, 0, 0);
+          if (on) colv = d < 7 ? cross3(rcol(s.body_R[a][bd], 2), p - ld3(s.body_x[a][bd])) : rcol(s.body_R[a][bd], 0);
+          for (int q = 0; q < 3; ++q) J[9 * q + d] = dot3(dirs[q], colv);
+        }
+        for (int q = 0; q < 3; ++q)
+          for (int i = 0; i < 9; ++i) { float acc = 0.f; for (int k = 0; k < 9; ++k) acc += s.Minv[a][9 * i + k] * J[9 * q + k]; Bv[9 * q + i] = acc; }
+      }
+    }
+    s.c_side[c] = sds[0] | (sds[1] << 13) | (armgeom ? (1 << 30) : 0);
+    s.c_g[c] = (g1 << 12) | g2;
+    st3(s.c_p[c], p); st3(s.c_n[c], n); s.c_mu[c] = mu;
+    float K, Bd, imp; impedance_f(pp + 1, pp + 3, dist, m.h, K, Bd, imp);
+    float dA = invw * (1.f + mu * mu);
+    float R0 = fmaxf(1e-15f, (1.f - imp) * dA / imp);
+    float Rpy = 2.f * mu * mu * R0;           // [3P] pyramidal regulariser
+    s.c_R[c] = Rpy;
+    SideW A, Bs;
+    side_prepare(s, m, sds[0], -1.f, p, n, t1, t2, A);
+    side_prepare(s, m, sds[1], +1.f, p, n, t1, t2, Bs);
+    // contact-space Delassus block W = sum_sides Jb Minv Jb^T  (xx,yy,zz,xy,xz,yz)
+    float W[6] = {0, 0, 0, 0, 0, 0};
+    const SideW* sw[2] = {&A, &Bs};
+    for (int q = 0; q < 2; ++q) {
+      const SideW& o = *sw[q];
+      if (o.type == FM_SIDE_CUBE) {
+        W[0] += o.invm + o.invI * dot3(o.ja[0], o.ja[0]); W[1] += o.invm + o.invI * dot3(o.ja[1], o.ja[1]); W[2] += o.invm + o.invI * dot3(o.ja[2], o.ja[2]);
+        W[3] += o.invI * dot3(o.ja[0], o.ja[1]); W[4] += o.invI * dot3(o.ja[0], o.ja[2]); W[5] += o.invI * dot3(o.ja[1], o.ja[2]);
+      } else if (o.type == FM_SIDE_BELT) {
+        float im = 1.0f / m.belt_mass;
+        W[0] += im * o.jb[0] * o.jb[0]; W[1] += im * o.jb[1] * o.jb[1]; W[2] += im * o.jb[2] * o.jb[2];
+        W[3] += im * o.jb[0] * o.jb[1]; W[4] += im * o.jb[0] * o.jb[2]; W[5] += im * o.jb[1] * o.jb[2];
+      } else if (o.type == FM_SIDE_ARM) {
+        float d00 = 0, d11 = 0, d22 = 0, d01 = 0, d02 = 0, d12 = 0;
+        for (int k = 0; k < 9; ++k) {
+          d00 += o.J[k] * o.B[k]; d11 += o.J[9 + k] * o.B[9 + k]; d22 += o.J[18 + k] * o.B[18 + k];
+          d01 += o.J[k] * o.B[9 + k]; d02 += o.J[k] * o.B[18 + k]; d12 += o.J[9 + k] * o.B[18 + k];
+        }
+        W[0] += d00; W[1] += d11; W[2] += d22; W[3] += d01; W[4] += d02; W[5] += d12;
+      }
+    }
+    for (int q = 0; q < 6; ++q) s.c_W[c][q] = W[q];
+    // velocity and warm-start acceleration in contact space
+    float uv[3] = {0, 0, 0}, ua[3] = {0, 0, 0};
+    side_dot<NA>(A, n, t1, t2, &s.belt_v, &s.cube_v[0][0], &s.arm_v[0][0], uv);
+    side_dot<NA>(Bs, n, t1, t2, &s.belt_v, &s.cube_v[0][0], &s.arm_v[0][0], uv);
+    float kid = K * imp * dist;
+    for (int r = 0; r < 4; ++r) {
+      int tq = 1 + (r >> 1); float cf = (r & 1) ? -mu : mu;
+      float vel = uv[0] + cf * uv[tq];
+      float aref = -Bd * vel - kid;
+      s.c_aref[c][r] = aref;
+      (void)ua;
+    }
+    // warm start: forces of the previous solve for the same contact (geom pair + index); binary search on sorted keys.
+    // (MuJoCo warm-starts the dual from qacc_warmstart as f = -jar/R; in fp32 that quotient is dominated by rounding.)
+    s.c_key[c] = key;
+    int lo = 0, hi = s.prev_n - 1, found = -1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; int pk = s.prev_key[mid]; if (pk == key) { found = mid; break; } if (pk < key) lo = mid + 1; else hi = mid - 1; }
+    for (int r = 0; r < 4; ++r) s.c_f[c][r] = found >= 0 ? s.prev_f[found][r] : 0.f;
+  }
+}
+
+// phase: arm-local rows (thread per arm): joint equality q_l - q_r = 0 and joint limits
+template <int NA, int E>
+FM_HD void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  for (int w = tid; w < NA * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int a = w / E;
+    int nr = 0;
+    {
+      float pos = s.arm_q[a][7] - s.arm_q[a][8];
+      float K, Bd, imp; impedance_f(m.eq_solref, m.eq_solimp, pos, m.h, K, Bd, imp);
+      float dA = m.ab_dofinvw[9] + m.ab_dofinvw[10];
+      float R = fmaxf(1e-15f, (1.f - imp) * dA / imp);
+      float vel = s.arm_v[a][7] - s.arm_v[a][8];
+      float aref = -Bd * vel - K * imp * pos;
+      s.arow_code[a][nr] = 0x1000; s.arow_aref[a][nr] = aref; s.arow_R[a][nr] = R;
+      s.arow_f[a][nr] = 0.f;
+      nr++;
+    }
+    for (int d = 0; d < 9; ++d) {
+      int b = dof_body(d);
+      float q = s.arm_q[a][d];
+      float dlo = q - m.ab_range[b][0], dhi = m.ab_range[b][1] - q;
+      for (int side = 0; side < 2; ++side) {
+        float dist = side ? dhi : dlo;
+        if (dist < 0.f) {
+          float sg = side ? -1.f : 1.f;
+          float K, Bd, imp; impedance_f(m.lim_solref, m.lim_solimp, dist, m.h, K, Bd, imp);
+          float R = fmaxf(1e-15f, (1.f - imp) * m.ab_dofinvw[b] / imp);
+          float aref = -Bd * sg * s.arm_v[a][d] - K * imp * dist;
+          s.arow_code[a][nr] = d | (side << 8); s.arow_aref[a][nr] = aref; s.arow_R[a][nr] = R;
+          s.arow_f[a][nr] = 0.f;
+          nr++;
+        }
+      }
+    }
+    s.arow_n[a] = nr;
+    for (int r = 0; r < nr; ++r)
+      for (int q = 0; q < s.prev_arow_n[a]; ++q) if (s.prev_arow_code[a][q] == s.arow_code[a][r]) s.arow_f[a][r] = s.prev_arow_f[a][q];
+  }
+}
+
+// phase: constraint islands (thread per env): union-find over cubes and arms, contact lists per island root
+template <int NA, int E>
+FM_HD void ph_islands(EnvS<NA>* S, int tid, int T) {
+  const int NN = EnvS<NA>::NNODE;
+  for (int w = tid; w < E; w += T) {
+    EnvS<NA>& s = S[w];
+    int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
+    s.ncon = nraw;
+    int root[NN];
+    for (int i = 0; i < NN; ++i) root[i] = i;
+    int node_of[FM_MAXCON];
+    for (int c = 0; c < nraw; ++c) {
+      int cs = s.c_side[c];
+      int nd[2] = {-1, -1};
+      for (int q = 0; q < 2; ++q) {
+        int sd = (cs >> (13 * q)) & 8191;
+        int ty = side_type(sd), ix = side_idx(sd);
+        if (ty == FM_SIDE_CUBE) nd[q] = ix; else if (ty == FM_SIDE_ARM) nd[q] = FM_NCUBE + (ix >> 4);
+      }
+      int x = nd[0] >= 0 ? nd[0] : nd[1];
+      node_of[c] = x;
+      if (nd[0] >= 0 && nd[1] >= 0) {
+        int ra = nd[0]; while (root[ra] != ra) ra = root[ra];
+        int rb = nd[1]; while (root[rb] != rb) rb = root[rb];
+        if (ra != rb) { if (ra < rb) root[rb] = ra; else root[ra] = rb; }
+      }
+    }
+    for (int i = 0; i < NN; ++i) { int r = i; while (root[r] != r) r = root[r]; root[i] = r; s.isl_root[i] = r; }
+    int cnt[NN + 1];
+    for (int i = 0; i <= NN; ++i) cnt[i] = 0;
+    for (int c = 0; c < nraw; ++c) if (node_of[c] >= 0) cnt[root[node_of[c]] + 1]++;
+    for (int i = 0; i < NN; ++i) cnt[i + 1] += cnt[i];
+    for (int i = 0; i <= NN; ++i) s.isl_start[i] = cnt[i];
+    for (int c = 0; c < nraw; ++c) if (node_of[c] >= 0) { int r = root[node_of[c]]; s.isl_list[cnt[r]++] = (unsigned char)c; }
+  }
+}
+
+// phase: actuation + smooth acceleration (mj_fwdActuation, mj_fwdAcceleration)
+template <int NA, int E>
+FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  const int per = 1 + FM_NCUBE + 9 * NA;
+  for (int w = tid; w < per * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int i = w / E;
+    if (i == 0) {
+      float c = clampf(s.ctrl_target[0], m.ctrl_lo[0], m.ctrl_hi[0]);
+      float f = m.belt_kv * (c - s.belt_v) - m.belt_damp * s.belt_v;
+      s.belt_acc_smooth = f / m.belt_mass; s.acc[0] = s.belt_acc_smooth; s.belt_S = 0.f;
+    } else if (i <= FM_NCUBE) {
+      float* a = &s.acc[1 + 6 * (i - 1)];
+      a[0] = 0; a[1] = 0; a[2] = -m.g; a[3] = 0; a[4] = 0; a[5] = 0;
+    } else {
+      int ad = i - 1 - FM_NCUBE; int a = ad / 9, r = ad % 9;
+      // row r of Minv * (tau - bias)
+      float tau[9];
+      for (int d = 0; d < 7; ++d) {
+        float c = clampf(s.ctrl_target[1 + 8 * a + d], m.ctrl_lo[1 + d], m.ctrl_hi[1 + d]);
+        tau[d] = m.kp * (c - s.arm_q[a][d]) - m.kd * s.arm_v[a][d] - s.bias[a][d];
+      }
+      float c = clampf(s.ctrl_target[1 + 8 * a + 7], m.ctrl_lo[8], m.ctrl_hi[8]);
+      float len = m.ten0 * s.arm_q[a][7] + m.ten1 * s.arm_q[a][8], lv = m.ten0 * s.arm_v[a][7] + m.ten1 * s.arm_v[a][8];
+      float f = clampf(m.g_kp * c - m.g_kb * len - m.g_kd * lv, m.g_fmin, m.g_fmax);
+      tau[7] = m.ten0 * f - s.bias[a][7]; tau[8] = m.ten1 * f - s.bias[a][8];
+      float acc = 0.f;
+      for (int k = 0; k < 9; ++k) acc += s.Minv[a][9 * r + k] * tau[k];
+      s.acc[61 + 9 * a + r] = acc;
+    }
+  }
+}
+
+// phase: projected Gauss-Seidel, one thread per constraint island
+template <int NA>
+FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool first, float& belt_sum) {
+  int cs = s.c_side[c];
+  f3 p = ld3(s.c_p[c]), n = ld3(s.c_n[c]); f3 t1, t2; make_frame3(n, t1, t2);
+  SideW A, B;
+  side_prepare(s, m, cs & 8191, -1.f, p, n, t1, t2, A);
+  side_prepare(s, m, (cs >> 13) & 8191, +1.f, p, n, t1, t2, B);
+  float mu = s.c_mu[c], R = s.c_R[c];
+  const float* W = s.c_W[c];
+  float f[4] = {s.c_f[c][0], s.c_f[c][1], s.c_f[c][2], s.c_f[c][3]};
+  float lam[3] = {0, 0, 0};
+  float maxd = 0.f;
+  if (first) {   // apply warm-start forces to the acceleration
+    lam[0] = f[0] + f[1] + f[2] + f[3]; lam[1] = mu * (f[0] - f[1]); lam[2] = mu * (f[2] - f[3]);
+  } else {
+    float u[3] = {0, 0, 0};
+    side_dot<NA>(A, n, t1, t2, &s.acc[0], &s.acc[1], &s.acc[61], u);
+    side_dot<NA>(B, n, t1, t2, &s.acc[0], &s.acc[1], &s.acc[61], u);
+    for (int r = 0; r < 4; ++r) {
+      int tq = 1 + (r >> 1); float cf = (r & 1) ? -mu : mu;
+      float Wnt = tq == 1 ? W[3] : W[4], Wtt = tq == 1 ? W[1] : W[2], Wtx = W[5];
+      float AR = W[0] + 2.f * cf * Wnt + cf * cf * Wtt + R;
+      float res = u[0] + cf * u[tq] - s.c_aref[c][r] + R * f[r];
+      float fn = fmaxf(0.f, f[r] - res / AR);
+      float df = fn - f[r];
+      f[r] = fn;
+      // contact-space acceleration update: u += W * (1, cf on tangent tq) * df
+      u[0] += (W[0] + cf * Wnt) * df;
+      u[tq] += (Wnt + cf * Wtt) * df;
+      u[3 - tq] += ((tq == 1 ? W[4] : W[3]) + cf * Wtx) * df;
+      lam[0] += df; lam[tq] += cf * df;
+      maxd = fmaxf(maxd, fabsf(df) * AR);
+    }
+    for (int r = 0; r < 4; ++r) s.c_f[c][r] = f[r];
+  }
+  side_apply<NA>(A, n, t1, t2, &s.acc[1], &s.acc[61], lam);
+  side_apply<NA>(B, n, t1, t2, &s.acc[1], &s.acc[61], lam);
+  // belt bookkeeping (lagged coupling): total contact-space force projected on the belt dof
+  if (A.type == FM_SIDE_BELT || B.type == FM_SIDE_BELT) {
+    const SideW& o = A.type == FM_SIDE_BELT ? A : B;
+    float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
+    belt_sum += o.sgn * (o.jb[0] * Fn + o.jb[1] * F1 + o.jb[2] * F2);
+  }
+  return maxd;
+}
+
+template <int NA>
+FM_HD float arm_rows_visit(EnvS<NA>& s, int a, bool first) {
+  float* acc = &s.acc[61 + 9 * a];
+  float maxd = 0.f;
+  for (int r = 0; r < s.arow_n[a]; ++r) {
+    int code = s.arow_code[a][r];
+    float R = s.arow_R[a][r], f = s.arow_f[a][r], df;
+    if (code & 0x1000) {
+      const float* Mi = s.Minv[a];
+      float AR = Mi[9 * 7 + 7] - 2.f * Mi[9 * 7 + 8] + Mi[9 * 8 + 8] + R;
+      if (first) df = f;
+      else { float res = acc[7] - acc[8] - s.arow_aref[a][r] + R * f; df = -res / AR; s.arow_f[a][r] = f + df; maxd = fmaxf(maxd, fabsf(df) * AR); }
+      for (int k = 0; k < 9; ++k) acc[k] += (Mi[9 * k + 7] - Mi[9 * k + 8]) * df;
+    } else {
+      int d = code & 255; float sg = (code >> 8) ? -1.f : 1.f;
+      const float* Mi = s.Minv[a];
+      float AR = Mi[9 * d + d] + R;
+      if (first) df = f;
+      else { float res = sg * acc[d] - s.arow_aref[a][r] + R * f; float fn = fmaxf(0.f, f - res / AR); df = fn - f; s.arow_f[a][r] = fn; maxd = fmaxf(maxd, fabsf(df) * AR); }
+      for (int k = 0; k < 9; ++k) acc[k] += sg * Mi[9 * k + d] * df;
+    }
+  }
+  return maxd;
+}
+
+template <int NA, int E>
+FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool first_outer, int inner, float tol) {
+  const int NN = EnvS<NA>::NNODE;
+  for (int w = tid; w < NN * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int node = w / E;
+    if (s.isl_root[node] != node) continue;
+    int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
+    bool has_arm = false;
+    for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
+    if (c0 == c1 && !has_arm) continue;
+    float belt_sum = 0.f;
+    if (first_outer) {
+      for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) arm_rows_visit(s, a, true);
+      for (int ci = c0; ci < c1; ++ci) contact_visit(s, m, s.isl_list[ci], true, belt_sum);
+    }
+    for (int it = 0; it < inner; ++it) {
+      float maxd = 0.f; belt_sum = 0.f;
+      for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, false));
+      for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, contact_visit(s, m, s.isl_list[ci], false, belt_sum));
+      if (maxd < tol) break;
+    }
+    if (belt_sum != 0.f) FM_ATOMIC_ADDF(&s.belt_S, belt_sum);
+  }
+}
+
+template <int NA, int E>
+FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  for (int w = tid; w < E; w += T) {
+    EnvS<NA>& s = S[w];
+    s.acc[0] = s.belt_acc_smooth + s.belt_S / m.belt_mass;
+    s.belt_S = 0.f;
+  }
+}
+
+// phase: force-termination statistic on the forces of this solve (base_env.py:226-236; clarification SURVEY.md A.2)
+template <int NA, int E>
+FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
+  for (int w = tid; w < FM_MAXCON * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int c = w / E;
+    if (c >= s.ncon || !((s.c_side[c] >> 30) & 1)) continue;
+    const float* f = s.c_f[c]; float mu = s.c_mu[c];
+    float v = fmaxf(fabsf(f[0] + f[1] + f[2] + f[3]), fmaxf(fabsf(mu * (f[0] - f[1])), fabsf(mu * (f[2] - f[3]))));
+    // float max via int compare (non-negative floats order like ints)
+    int vi; memcpy(&vi, &v, 4);
+    FM_ATOMIC_MAXI((int*)&s.force_max, vi);
+  }
+}
+
+// phase: implicitfast velocity update + semi-implicit position integration (mj_implicit, mj_advance) [3P]
+template <int NA, int E>
+FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  const int per = 1 + FM_NCUBE + NA;
+  for (int w = tid; w < per * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int i = w / E;
+    float h = m.h;
+    if (i == 0) {
+      float a = s.acc[0];
+      s.acc_ws[0] = a;
+      float ai = m.belt_mass * a / (m.belt_mass + h * (m.belt_kv + m.belt_damp));
+      s.belt_v += h * ai; s.belt_q += h * s.belt_v;
+    } else if (i <= FM_NCUBE) {
+      int k = i - 1;
+      float* a = &s.acc[1 + 6 * k]; float* v = s.cube_v[k]; float* q = s.cube_q[k];
+      for (int d = 0; d < 6; ++d) { s.acc_ws[1 + 6 * k + d] = a[d]; v[d] += h * a[d]; }
+      q[0] += h * v[0]; q[1] += h * v[1]; q[2] += h * v[2];
+      f3 wv = mk3(v[3], v[4], v[5]);
+      float wn = norm3(wv);
+      q4 qq = qnormf(mkq(q[3], q[4], q[5], q[6]));
+      if (wn > 0.f) {
+        float sn, cs; sincosf(0.5f * wn * h, &sn, &cs);
+        f3 ax = wv * (sn / wn);
+        qq = qmulf(qq, mkq(cs, ax.x, ax.y, ax.z));
+      }
+      q[3] = qq.w; q[4] = qq.x; q[5] = qq.y; q[6] = qq.z;
+    } else {
+      int a = i - 1 - FM_NCUBE;
+      float* acc = &s.acc[61 + 9 * a];
+      float y[9];
+      for (int r = 0; r < 9; ++r) {
+        float sum = 0.f;
+        for (int k = 0; k < 9; ++k) sum += s.M[a][r >= k ? tri(r, k) : tri(k, r)] * acc[k];
+        y[r] = sum; s.acc_ws[61 + 9 * a + r] = acc[r];
+      }
+      chol9_solve(s.Li[a], y);
+      for (int r = 0; r < 9; ++r) { s.arm_v[a][r] += h * y[r]; s.arm_q[a][r] += h * s.arm_v[a][r]; }
+    }
+  }
+}
+
+// phase: remember this solve's forces for the next warm start
+template <int NA, int E>
+FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
+  for (int w = tid; w < (FM_MAXCON + NA) * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int c = w / E;
+    if (c < FM_MAXCON) {
+      if (c == 0) s.prev_n = s.ncon;
+      if (c < s.ncon) { s.prev_key[c] = s.c_key[c]; for (int r = 0; r < 4; ++r) s.prev_f[c][r] = s.c_f[c][r]; }
+    } else {
+      int a = c - FM_MAXCON;
+      s.prev_arow_n[a] = s.arow_n[a];
+      for (int r = 0; r < s.arow_n[a]; ++r) { s.prev_arow_code[a][r] = s.arow_code[a][r]; s.prev_arow_f[a][r] = s.arow_f[a][r]; }
+    }
+  }
+}
+
+// phase: PT1 control filter (base_env.py:209-215) and per-substep counters reset
+template <int NA, int E>
+FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float alpha) {
+  const int NU = EnvS<NA>::NU;
+  for (int w = tid; w < NU * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int u = w / E;
+    if (u == 0) { s.ctrl_target[0] = -s.conveyor_speed; }
+    else s.ctrl_target[u] += (s.ctrl[u] - s.ctrl_target[u]) * alpha;
+  }
+}
+template <int NA, int E>
+FM_HD void ph_clear(EnvS<NA>* S, int tid, int T) {
+  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.n_armside = 0; s.nqueue = 0; s.ncon = 0; }
+}

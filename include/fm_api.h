@@ -1,0 +1,85 @@
+/* fm_api.h — C-ABI of the B200 batched TaskEnv library (libfm_b200.so).
+ *
+ * The reference (nkirschi/Factory-MARL) has no FFI; its seam for this path is the Python env contract consumed
+ * by stable-baselines3.  Each entry point below names the reference interface it replaces.
+ * All pointers except `blob`, `cfg` and the debug outputs are DEVICE pointers owned by the caller; the library
+ * owns only the handle and the device copies of the model constants.  Calls are stream-ordered on `stream`
+ * (a cudaStream_t passed as void*), made from one host thread per GPU.  Return value: 0 = OK, non-zero = error,
+ * message via fm_last_error().  Nothing throws across the ABI.
+ */
+#ifndef FM_API_H
+#define FM_API_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fm_handle fm_handle;
+
+/* env_class: the 7 env classes of src/environments.py (FM_ENV_* order = inheritance listing environments.py:13-22) */
+enum { FM_FACTORY_MANIPULATION_ENV = 0, FM_SINGLE_FULL_RL = 1, FM_SINGLE_DELTA = 2, FM_ALL_FULL_RL = 3, FM_ALL_DELTA = 4,
+       FM_PAUSE_IK_TOGGLE = 5, FM_BACKUP_IK_TOGGLE = 6 };
+
+/* BaseEnv.__init__ kwargs (challenge_env/challenge_env/base_env.py:15-35) + ProgressRewardEnv weights
+ * (src/environments.py:252-259) + solver knobs of this implementation. */
+typedef struct fm_config {
+  int32_t n_envs, n_arms, env_class, auto_reset;
+  int32_t pgs_outer, pgs_inner, envs_per_block, reserved;
+  float pgs_tol, reserved_f;
+  double initial_conveyor_speed, conveyor_acceleration, pt_time, force_contact_threshold, control_frequency,
+      spawn_freq, spawn_freq_increase;
+  double gripper_to_closest_cube_reward_factor, closest_cube_to_bucket_reward_factor, small_action_norm_reward_factor,
+      base_reward;
+} fm_config;
+
+/* one env's physics state in the reference's (MuJoCo) layout; host pointers (parity tests on identical qpos/qvel/ctrl) */
+typedef struct fm_state_view {
+  int32_t env;
+  double* qpos;        /* [nq]  = 1 + 7*10 + 9*n_arms    */
+  double* qvel;        /* [nv]  = 1 + 6*10 + 9*n_arms */
+  double* ctrl_target; /* [nu]  = 1 + 8*n_arms          (BaseEnv.ctrl_target, base_env.py:187) */
+} fm_state_view;
+
+/* debug view of one env after the first sub-step's position stage (tests only) */
+typedef struct fm_debug_view {
+  int32_t env, ncon, flags, reserved;
+  int32_t pair[64][2];          /* geom ids (MuJoCo numbering of the compiled scene), sorted */
+  float pos[64][3], normal[64][3], force[64][4];
+  float site_xpos[4][3];
+  float mass_matrix[4][45];     /* packed lower triangle of each arm's 9x9 block */
+  float bias[4][9];
+  float qacc_smooth[97], qacc[97];
+} fm_debug_view;
+
+/* BaseEnv.__init__ + build_scene (base_env.py:15-147, scene.py:109-169): model_blob from factory_marl_b200.model.build_blob */
+int fm_create(const fm_config* cfg, const void* model_blob, size_t n, fm_handle** out);
+int fm_destroy(fm_handle* h);                                       /* BaseEnv.close (base_env.py:293-295) */
+int fm_obs_dim(const fm_handle* h);                                 /* observation_space.shape (environments.py:41-46,553-558) */
+int fm_act_dim(const fm_handle* h);                                 /* action_space (environments.py:399-403,474-479,549) */
+/* rows of the caller-allocated SoA state arrays [rows][n_envs]: float32, float64, int32 (uint64 rng is always 4 rows) */
+int fm_state_rows(const fm_handle* h, int32_t* nf, int32_t* nd, int32_t* ni);
+int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng);
+/* field offsets inside the SoA arrays, by name (e.g. "F_ARM_Q", "I_SCORE", "I_IGNORE"); -1 if unknown */
+int fm_field_offset(const fm_handle* h, const char* name);
+/* FactoryManipulationEnv.reset / BaseEnv.reset_sim (environments.py:204-248, base_env.py:177-198); mask [N] or NULL = all */
+int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream);
+/* FactoryManipulationEnv.step (environments.py:151-202) for all envs, with SB3-VecEnv auto-reset when cfg.auto_reset:
+ * actions f32[N, act_dim] (Box) or i32[N, n_arms] (MultiDiscrete); flags bit0 out_of_reach, bit1 force_terminate,
+ * bits 2.. capacity overflow diagnostics; ep_info [N,4] = episode return, length, score0, score1 (Monitor + ep_score_history) */
+int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores,
+            uint8_t* flags, float* terminal_obs, float* ep_info, void* stream);
+/* IK base policy for all arms: IKPolicy.act + FactoryManipulationEnv._compose_control (ik_policy.py:141-282,
+ * environments.py:104-127).  Writes the proposals into the state (used by the next fm_step) and, for the toggling
+ * envs, into obs[:, base_dim:] (IKTogglingEnv._process_observation, environments.py:560-577). */
+int fm_ik_policy(fm_handle* h, float* obs, void* stream);
+int fm_get_state(fm_handle* h, fm_state_view* v);                   /* physics.data.qpos/qvel, BaseEnv.ctrl_target */
+int fm_set_state(fm_handle* h, const fm_state_view* v);
+/* run n raw sub-steps (mj_step2 + mj_step1 each) with ctrl = ctrl_target, no filter, no task logic; dump env `view->env` */
+int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void* stream);
+const char* fm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

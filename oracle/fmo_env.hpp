@@ -385,7 +385,8 @@ struct Env {
     }
   }
   void process_action(const float* a, double* out) {   // environments.py:84-102
-    for (int k = 0; k < 8; ++k) { double t = std::tanh((double)a[k]); out[k] = lo(k) + (t + 1.0) * 0.5 * (hi(k) - lo(k)); }
+    // np.tanh of a float32 array stays float32, as does (a + 1.0) * 0.5; the product with (high - low) promotes to float64
+    for (int k = 0; k < 8; ++k) { float t = std::tanh((float)a[k]); float u = (t + 1.0f) * 0.5f; out[k] = lo(k) + (double)u * (hi(k) - lo(k)); }
   }
   void compose_control(const float* af, const int* ai, std::vector<double>& acts) {
     double pa[8];

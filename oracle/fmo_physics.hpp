@@ -513,7 +513,7 @@ static int box_box(V3 p1, const M3& R1, const double* A, V3 p2, const M3& R2, co
     double e = dot(col(R2, j), pw);
     double s = std::fabs(e) - (B[j] + A[0] * Q[j] + A[1] * Q[3 + j] + A[2] * Q[6 + j]);
     if (s > 0) return 0;
-    if (s > best + 1e-9) { best = s; code = 3 + j; flip = e < 0; nbest = col(R2, j); }
+    if (s > best + 1e-6) { best = s; code = 3 + j; flip = e < 0; nbest = col(R2, j); }
   }
   // edge x edge axes
   const double fudge = 1.05;
@@ -521,17 +521,14 @@ static int box_box(V3 p1, const M3& R1, const double* A, V3 p2, const M3& R2, co
     for (int j = 0; j < 3; ++j) {
       V3 ax = cross(col(R1, i), col(R2, j));
       double l = norm(ax);
-      if (l < 1e-6) continue;
+      if (l < 1e-4) continue;
       ax = ax * (1.0 / l);
       double e = dot(ax, pw);
       double ra = 0, rb = 0;
       for (int k = 0; k < 3; ++k) { ra += A[k] * std::fabs(dot(ax, col(R1, k))); rb += B[k] * std::fabs(dot(ax, col(R2, k))); }
       double s = std::fabs(e) - (ra + rb);
       if (s > 0) return 0;
-      if (s * fudge > best + 1e-9 && s > best) {
-        // prefer faces unless the edge axis is clearly better
-        if (s > best * (1.0 / fudge) || best < -1e200) { best = s; code = 6 + 3 * i + j; flip = e < 0; nbest = ax; }
-      }
+      if (s > best * (1.0 / fudge) + 1e-6) { best = s; code = 6 + 3 * i + j; flip = e < 0; nbest = ax; }
     }
   V3 n = flip ? nbest * -1.0 : nbest;   // from box1 towards box2
   double depth = -best;
@@ -548,7 +545,7 @@ static int box_box(V3 p1, const M3& R1, const double* A, V3 p2, const M3& R2, co
     double uaub = dot(ua, ub), q1 = dot(ua, dp), q2 = -dot(ub, dp);
     double dn = 1 - uaub * uaub;
     double al = 0, be = 0;
-    if (dn > 1e-12) { al = (q1 + uaub * q2) / dn; be = (uaub * q1 + q2) / dn; }
+    if (dn > 1e-8) { al = (q1 + uaub * q2) / dn; be = (uaub * q1 + q2) / dn; }
     al = std::min(std::max(al, -A[i]), A[i]); be = std::min(std::max(be, -B[j]), B[j]);
     V3 ca = pa + ua * al, cb = pb + ub * be;
     out[0] = {(ca + cb) * 0.5, n, -depth};

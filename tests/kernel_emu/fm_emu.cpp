@@ -1,0 +1,93 @@
+// fm_emu.cpp — HOST-COMPILED LOGIC-TEST BUILD of the step kernel's phase functions (tests only, never shipped).
+// It exports the same C-ABI as the CUDA library (include/fm_api.h) but every pointer is a host pointer and every
+// barrier interval is executed as a loop over thread ids.  Purpose: exercise the exact device source
+// (factory_marl_b200/csrc/fm_*.cuh) against the fp64 oracle in `-m "not gpu"` tests, where no GPU exists.
+// The product (factory_marl_b200/) never loads this library; its ops fail loudly without the CUDA build.
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+#include <vector>
+#include "../../factory_marl_b200/csrc/fm_host_common.h"
+#include "../../factory_marl_b200/csrc/fm_ik.cuh"
+
+static thread_local std::string g_err;
+struct HostRun { int T; template <class F> void operator()(F f) { for (int t = 0; t < T; ++t) f(t); } };
+
+struct fm_handle {
+  FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st; int E;
+  std::vector<char> smem;
+};
+
+template <int NA, int E>
+static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
+  HostRun run{32 * E};
+  size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS)) + 64;
+  if (h->smem.size() < need) h->smem.resize(need);
+  int nblk = (h->cfg.n_envs + E - 1) / E;
+  for (int b = 0; b < nblk; ++b) {
+    memset(h->smem.data(), 0, need);
+    EnvS<NA>* S = (EnvS<NA>*)h->smem.data(); TaskS* TS = (TaskS*)(S + E);
+    fm_block_step<NA, E>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
+  }
+}
+static void dispatch(fm_handle* h, const FmStepArgs& ar) {
+  if (h->hm.n_arms == 2) { if (h->E == 8) run_blocks<2, 8>(h, ar); else run_blocks<2, 4>(h, ar); }
+  else run_blocks<4, 4>(h, ar);
+}
+
+extern "C" {
+const char* fm_last_error(void) { return g_err.c_str(); }
+int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {
+  try {
+    fm_handle* h = new fm_handle();
+    fm_build_host_model(blob, n, h->hm);
+    if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
+    if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
+    h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
+    h->E = (h->hm.n_arms == 2 && cfg->envs_per_block == 8) ? 8 : 4;
+    h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs};
+    *out = h; return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+int fm_destroy(fm_handle* h) { delete h; return 0; }
+int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : Lay<4>::obs_dim(h->cfg.env_class); }
+int fm_act_dim(const fm_handle* h) { return fm_act_dim_of(h->cfg.env_class, h->hm.n_arms); }
+int fm_state_rows(const fm_handle* h, int32_t* nf, int32_t* nd, int32_t* ni) {
+  if (h->hm.n_arms == 2) { *nf = Lay<2>::NF; *nd = Lay<2>::ND; *ni = Lay<2>::NI; } else { *nf = Lay<4>::NF; *nd = Lay<4>::ND; *ni = Lay<4>::NI; }
+  return 0;
+}
+int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng) { h->st.f = f; h->st.d = d; h->st.i = i; h->st.rng = (unsigned long long*)rng; return 0; }
+int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : fm_field_offset_t<4>(name); }
+int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void*) {
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.reset_mask = mask; ar.obs = obs;
+  dispatch(h, ar); return 0;
+}
+int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores, uint8_t* flags,
+            float* terminal_obs, float* ep_info, void*) {
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar));
+  ar.mode = 0; ar.act_f = (const float*)actions; ar.act_i = (const int*)actions; ar.obs = obs; ar.reward = reward; ar.terminated = terminated;
+  ar.scores = scores; ar.flags = flags; ar.terminal_obs = terminal_obs; ar.ep_info = ep_info; ar.auto_reset = h->user.auto_reset;
+  dispatch(h, ar); return 0;
+}
+int fm_ik_policy(fm_handle* h, float* obs, void*) {
+  int N = h->cfg.n_envs, od = fm_obs_dim(h);
+  for (int e = 0; e < N; ++e) {
+    if (h->hm.n_arms == 2) fm_ik_env<2>(h->hm.ik, h->cfg, h->st, obs, od, e);
+    else fm_ik_env<4>(h->hm.ik, h->cfg, h->st, obs, od, e);
+  }
+  return 0;
+}
+int fm_get_state(fm_handle* h, fm_state_view* v) { if (h->hm.n_arms == 2) fm_view_get<2>(h->st.f, h->st.n, v); else fm_view_get<4>(h->st.f, h->st.n, v); return 0; }
+int fm_set_state(fm_handle* h, const fm_state_view* v) {
+  if (h->hm.n_arms == 2) { fm_view_set<2>(h->st.f, h->st.n, v); fm_view_clear_warm<2>(h->st.i, h->st.n, v->env); }
+  else { fm_view_set<4>(h->st.f, h->st.n, v); fm_view_clear_warm<4>(h->st.i, h->st.n, v->env); }
+  return 0;
+}
+int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void*) {
+  FmDebugDump* d = new FmDebugDump(); memset(d, 0, sizeof(*d)); d->env = view ? view->env : -1;
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? d : nullptr;
+  dispatch(h, ar);
+  if (view) { if (h->hm.n_arms == 2) fm_dump_to_view<2>(*d, view); else fm_dump_to_view<4>(*d, view); }
+  delete d; return 0;
+}
+}
