@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the batched TaskEnv hot path (BASELINE.json: env-steps/s; PPO samples/s).
+
+  python bench.py --gpus N --steps K --warmup W            ours: CUDA step kernel (+ on-GPU policy), one rank per GPU
+  python bench.py --impl reference --gpus N ...            reference arm: the fp64 CPU restatement (oracle port) on host cores
+
+A "step" is one control step (100 physics sub-steps + task logic + obs/reward) of every env of the workload
+`4096 batched TaskEnv (AllFullRLProgressRewardEnv map), two arms, fixed random policy` (BASELINE.json configs[1])
+per GPU (weak scaling: 4096 envs per rank, env shards independent, no data-path collective).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_CLASS = "AllFullRLProgressRewardEnv"
+ENV_KW = dict(gripper_to_closest_cube_reward_factor=0.2, closest_cube_to_bucket_reward_factor=0.4, base_reward=0.4)  # runs/rk5rxnav.json:25-41
+N_ENVS_PER_GPU = 4096
+METRIC = "batched TaskEnv env-steps/sec"
+UNIT = "env-steps/s"
+# algorithmic work per env-step (DESIGN.md "Measurement"): state in+out + action + obs + scalars, fp32 flop hand count
+FLOP_PER_ENV_STEP = 2.1e7
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.reasons, self.stop_flag, self.max_mhz = gpu_index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:6]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def _cpu_worker(args):
+    seed, n_steps, warm = args
+    from factory_marl_b200 import model as fm
+    from oracle.oracle_py import Oracle
+    o = Oracle(fm.build_blob(2))
+    o.env_create(ENV_CLASS, seed=42 + seed, **ENV_KW)
+    o.env_reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, (warm + n_steps, 16)).astype(np.float32)
+    for t in range(warm):
+        _, _, info = o.env_step(acts[t])
+        if info["terminated"]:
+            o.env_reset()
+    t0 = time.perf_counter()
+    for t in range(n_steps):
+        _, _, info = o.env_step(acts[warm + t])
+        if info["terminated"]:
+            o.env_reset()
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(steps_per_env: int, warm: int = 3):
+    """The fp64 CPU restatement of the reference path (oracle/), one env per host core, all cores, wall clock.
+    The real reference (Python + dm_control + MuJoCo + SubprocVecEnv pipes) cannot run in this image;
+    this port has none of that overhead."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(i, steps_per_env, warm) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    rate = cores * steps_per_env / max(times)
+    return rate, cores, f"{cores} envs x {steps_per_env} control steps (100 sub-steps each) of the bench workload, one env per core, seeded random actions", wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 4           # control steps per env per "step" of this arm (bounded sample)
+    K, W = args.steps, args.warmup
+    rate, cores, sample, wall = cpu_reference_rate(per_step * K, warm=max(1, W))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * cores * per_step / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{ENV_CLASS}, 2 arms, seeded random actions, fp64 CPU restatement of MuJoCo TaskEnv (the reference's MuJoCo/dm_control/SB3 stack is not installable here)",
+                       "envs": cores, "steps_per_env_per_step": per_step},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    from factory_marl_b200 import ppo as fppo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    K, W = args.steps, max(args.warmup, 3)
+    env = FactoryVecEnv(ENV_CLASS, num_envs=n, num_arms=2, seeds=list(range(42 + rank * n, 42 + (rank + 1) * n)),
+                        device=dev, **ENV_KW)
+    # fixed random policy: freshly initialised 178->128->128->16 tanh MLP, orthogonal init, torch seed 0, log_std = 0
+    pol = fppo.PolicyValueNet(env.core.obs_dim, env.core.act_dim, discrete=False, device=dev, seed=0)
+    obs = env.reset()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def one_step(o):
+        act = pol.act(o)                    # on-GPU MLP forward + Gaussian sample, clipped to [-1, 1] as SB3 does
+        o2, rew, term, _ = env.step(act)
+        return o2
+
+    for _ in range(W):
+        obs = one_step(obs)
+    torch.cuda.synchronize()
+    l0 = env.gpu_launches + pol.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.fill_(float(k))               # L2 flush between timed iterations (outside the per-step event pairs)
+        ev[k][0].record()
+        act = pol.act(obs)
+        ev[k][1].record()
+        obs, rew, term, _ = env.step(act)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
+    kern_ms = sum(b.elapsed_time(c) for a, b, c in ev) / K      # the dominant kernel: fm_step_kernel
+    launches = env.gpu_launches + pol.launches - l0
+    t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- e2e: through the public VecEnv API with HOST buffers (pinned), H2D actions + D2H obs/reward/done every step
+    host_act = torch.empty((n, 16), dtype=torch.float32).pin_memory()
+    host_act.copy_(torch.from_numpy(np.random.default_rng(rank).uniform(-1, 1, (n, 16)).astype(np.float32)))
+    host_obs = torch.empty((n, env.core.obs_dim), dtype=torch.float32).pin_memory()
+    host_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
+    host_done = torch.empty((n,), dtype=torch.bool).pin_memory()
+    Ke = max(3, min(K, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(Ke):
+        a_dev = host_act.to(dev, non_blocking=True)
+        o2, rew, term, _ = env.step(a_dev)
+        host_obs.copy_(o2, non_blocking=True); host_rew.copy_(rew, non_blocking=True); host_done.copy_(term, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the user reads the result on the host every step
+    e1.record(); torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / (float(te.item()) * 1e-3)
+    h2d = host_act.numel() * 4
+    d2h = host_obs.numel() * 4 + host_rew.numel() * 4 + host_done.numel()
+
+    if rank == 0:
+        hbm_peak, peak_kind, sm_max = peaks()
+        nf, nd, ni = env.core.f.shape[0], env.core.d.shape[0], env.core.i.shape[0]
+        bytes_per_env = 2 * (4 * nf + 8 * nd + 4 * ni) + 4 * 16 + 4 * env.core.obs_dim + 4 + 1 + 8 + 1 + 16
+        ach = bytes_per_env * n / (kern_ms * 1e-3) / 1e9
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{n} batched TaskEnv per GPU ({ENV_CLASS} action map), two arms, fixed random policy (178-128-128-16 tanh MLP, seed 0), 100 sub-steps per step",
+                           "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB write)", "pgs": [env.core.cfg.pgs_outer, env.core.cfg.pgs_inner]},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                             "peak_source": peak_kind, "kernel": "fm_step_kernel", "kernel_ms": kern_ms, "bytes_per_env_step": bytes_per_env,
+                             "note": "the step kernel is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); see roofline_fp32"},
+                "roofline_fp32": {"achieved": FLOP_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                  "frac": FLOP_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e12 / fp32_peak, "flop_per_env_step": FLOP_PER_ENV_STEP,
+                                  "peak_source": "148 SM x 128 lanes x 2 x max SM clock"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": sampler.result()}
+        if world == 1 and not args.no_cpu:
+            rate, cores, sample, wall = cpu_reference_rate(args.cpu_steps)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,7 +72,7 @@ class FmCore:
     to_numpy(array)->np.ndarray, from_numpy(np)->array and stream()->int."""
 
     def __init__(self, lib, backend, blob: bytes, num_envs: int, num_arms: int, env_class, seeds=None, auto_reset=True,
-                 pgs_outer=0, pgs_inner=0, pgs_tol=0.0, envs_per_block=0, initial_conveyor_speed=0.1,
+                 pgs_outer=0, pgs_inner=0, pgs_tol=0.0, envs_per_block=0, sleep_hidden=True, initial_conveyor_speed=0.1,
                  conveyor_acceleration=0.001, pt_time=0.2, force_contact_threshold=200.0, control_frequency=10,
                  spawn_freq=1 / 10, spawn_freq_increase=1.001, gripper_to_closest_cube_reward_factor=0.0,
                  closest_cube_to_bucket_reward_factor=0.0, small_action_norm_reward_factor=0.0, base_reward=0.0):
@@ -81,6 +81,7 @@ class FmCore:
         self.num_envs, self.num_arms = int(num_envs), int(num_arms)
         self.cfg = fm_config(n_envs=num_envs, n_arms=num_arms, env_class=self.env_class, auto_reset=int(auto_reset),
                              pgs_outer=pgs_outer, pgs_inner=pgs_inner, envs_per_block=envs_per_block, pgs_tol=pgs_tol,
+                             reserved=0 if sleep_hidden else 1,
                              initial_conveyor_speed=initial_conveyor_speed, conveyor_acceleration=conveyor_acceleration,
                              pt_time=pt_time, force_contact_threshold=force_contact_threshold,
                              control_frequency=control_frequency, spawn_freq=spawn_freq,
@@ -159,7 +160,7 @@ class FmCore:
     def reset(self, mask=None):
         be = self.be
         self._chk(self.lib.fm_reset(self.h, be.ptr(mask) if mask is not None else None, be.ptr(self.obs), be.stream()))
-        if self.uses_ik:
+        if self.is_toggle:       # IKTogglingEnv._process_observation also runs at reset (environments.py:244)
             self._chk(self.lib.fm_ik_policy(self.h, be.ptr(self.obs), be.stream()))
         return self.obs
 
@@ -170,6 +171,17 @@ class FmCore:
                                    be.ptr(self.scores), be.ptr(self.flags), be.ptr(self.terminal_obs), be.ptr(self.ep_info),
                                    be.stream()))
         return self.obs, self.reward, self.terminated
+
+    def env_step(self, actions):
+        """One FactoryManipulationEnv.step for every env, with the IK base policy run where the reference runs it:
+        before the step for the base / Single* / *Delta classes (environments.py:120-127,419,456,531), inside
+        _process_observation (after the step) for the toggling classes (environments.py:574-576)."""
+        if self.env_class in (0, 1, 2, 4):
+            self.ik_policy(write_obs=False)
+        out = self.step(actions)
+        if self.is_toggle:
+            self.ik_policy(write_obs=True)
+        return out
 
     def ik_policy(self, write_obs=True):
         be = self.be

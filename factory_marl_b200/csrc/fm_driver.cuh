@@ -31,12 +31,12 @@ struct FmStepArgs {
 };
 
 template <int NA, int E, class Run>
-FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned short* cpairs, const int* geom_class, int T) {
-  run([&](int tid) { ph_clear<NA, E>(S, tid, T); ph_cube_derive<NA, E>(S, tid, T); ph_arm_fk<NA, E>(S, m, tid, T, true); });
+FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class, int T, int sleep_hidden) {
+  run([&](int tid) { ph_clear<NA, E>(S, tid, T); ph_cube_derive<NA, E>(S, m, tid, T, sleep_hidden); ph_arm_fk<NA, E>(S, m, tid, T, true); });
   run([&](int tid) { ph_arm_body<NA, E>(S, m, tid, T); });
   run([&](int tid) { ph_arm_backward<NA, E>(S, m, tid, T); ph_broad<NA, E>(S, m, cpairs, tid, T); });
-  run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); ph_narrow<NA, E>(S, m, cpairs, tid, T); });
-  run([&](int tid) { ph_arm_chol<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_arm_chol<NA, E>(S, m, tid, T); ph_narrow<NA, E>(S, m, cpairs, tid, T); });   // raw contacts reuse the arm scratch
   run([&](int tid) { ph_arm_minv<NA, E>(S, tid, T); });
   run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T); ph_arm_rows<NA, E>(S, m, tid, T); });
 }
@@ -67,7 +67,7 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
 }
 
 template <int NA, int E, class Run>
-FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const unsigned short* cpairs, const int* geom_class,
+FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class,
                          const FmEnvCfg& cfg, const FmStatePtrs& st, const FmStepArgs& ar, int env0) {
   const int T = 32 * E;
   typedef Lay<NA> L;
@@ -93,21 +93,19 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
   else run([&](int tid) {   // debug: ctrl_target is used as is (no filter): ctrl := ctrl_target
     for (int w = tid; w < EnvS<NA>::NU * E; w += T) S[w % E].ctrl[w / E] = S[w % E].ctrl_target[w / E];
   });
-  fm_derive<NA, E>(run, S, m, cpairs, geom_class, T);
+  fm_derive<NA, E>(run, S, m, cpairs, geom_class, T, cfg.sleep_hidden);
   run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
   const double hd = cfg.dt / cfg.frame_skip;
   const float alpha = (float)(hd / (hd + cfg.pt_time));   // base_env.py:209-211
   const int nsub = ar.mode == 0 ? cfg.frame_skip : ar.n_substeps;
   for (int t = 0; t < nsub; ++t) {
-    if (t > 0) fm_derive<NA, E>(run, S, m, cpairs, geom_class, T);
-    run([&](int tid) { ph_islands<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, alpha); });
+    if (t > 0) fm_derive<NA, E>(run, S, m, cpairs, geom_class, T, cfg.sleep_hidden);
+    run([&](int tid) { ph_island_union<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, alpha); });
+    run([&](int tid) { ph_island_lists<NA, E>(S, tid, T); ph_smooth<NA, E>(S, m, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
-    run([&](int tid) { ph_smooth<NA, E>(S, m, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 1); });
-    for (int o = 0; o < cfg.pgs_outer; ++o) {
-      run([&](int tid) { ph_pgs<NA, E>(S, m, tid, T, o == 0, cfg.pgs_inner, cfg.pgs_tol); });
-      run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); });
-    }
+    run([&](int tid) { ph_pgs<NA, E>(S, m, tid, T, cfg.pgs_inner, cfg.pgs_tol); });
+    run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 2); });
     run([&](int tid) { if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });
   }

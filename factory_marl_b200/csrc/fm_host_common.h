@@ -16,7 +16,8 @@ inline FmEnvCfg fm_make_cfg(const fm_config& c, double h) {
   e.dt = h * e.frame_skip;                                               // base_env.py:201
   e.pgs_outer = c.pgs_outer > 0 ? c.pgs_outer : 2;
   e.pgs_inner = c.pgs_inner > 0 ? c.pgs_inner : 8;
-  e.pgs_tol = c.pgs_tol > 0 ? c.pgs_tol : 1e-6f;
+  e.sleep_hidden = c.reserved == 0 ? 1 : 0;          // fm_config.reserved: 0 = sleep resting hidden cubes (default), 1 = keep them live
+  e.pgs_tol = c.pgs_tol > 0 ? c.pgs_tol : 1e-3f;      // m/s^2: below the fp32 noise floor of the stiff rows
   e.initial_conveyor_speed = c.initial_conveyor_speed; e.conveyor_acceleration = c.conveyor_acceleration;
   e.pt_time = c.pt_time; e.force_threshold = c.force_contact_threshold;
   e.init_spawn_freq = c.spawn_freq * c.n_arms;                            // base_env.py:36
@@ -87,7 +88,6 @@ inline void fm_view_set(float* f, int N, const fm_state_view* v) {
     for (int k = 0; k < 9 * NA; ++k) W(L::F_ARM_V + k, v->qvel[61 + k]);
   }
   if (v->ctrl_target) for (int k = 0; k < 1 + 8 * NA; ++k) W(L::F_CTRL_T + k, v->ctrl_target[k]);
-  for (int k = 0; k < L::NV; ++k) W(L::F_ACC_WS + k, 0.0);
 }
 template <int NA>
 inline void fm_view_clear_warm(int* i, int N, int env) { typedef Lay<NA> L; i[(size_t)L::I_PREV_N * N + env] = 0; for (int a = 0; a < NA; ++a) i[(size_t)(L::I_PREV_AN + a) * N + env] = 0; }

@@ -4,13 +4,14 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <cmath>
 #include "../../include/fm_blob.h"
 #include "fm_types.h"
 
 struct FmHostModel {
   FmDevModel dm;
   FmIkModel ik;
-  std::vector<unsigned short> cpairs;   // 2 per cluster pair
+  std::vector<unsigned int> cpairs;     // packed pair records: c1 | c2 << 8 | test type << 16 (big-vs-big pairs resolved here)
   std::vector<int> geom_class;
   int n_arms = 0, nq = 0, nv = 0, nu = 0, ngeom = 0;
   double timestep = 0.001;   // fp64 copy: frame_skip = int((1/control_frequency)/timestep) must be evaluated in double
@@ -140,8 +141,37 @@ inline void fm_build_host_model(const void* blob, size_t n, FmHostModel& H) {
   m.n_cluster = (int)(c / 2);
   if (m.n_cluster > (int)(sizeof(m.cl_kind) / sizeof(int))) throw std::runtime_error("too many clusters");
   for (int i = 0; i < m.n_cluster; ++i) { m.cl_kind[i] = clk[2 * i]; m.cl_idx[i] = clk[2 * i + 1]; }
+  // conservative world AABBs of the big geoms (rotated boxes: |R| * half); the belt slides along +y over its whole length
+  m.cl_sph0 = m.n_sbox + 2;
+  for (int i = 0; i < m.n_sbox; ++i)
+    for (int ax = 0; ax < 3; ++ax) {
+      float e = fabsf(m.sbox_R[i][3 * ax]) * m.sbox_half[i][0] + fabsf(m.sbox_R[i][3 * ax + 1]) * m.sbox_half[i][1] + fabsf(m.sbox_R[i][3 * ax + 2]) * m.sbox_half[i][2];
+      m.big_aabb[1 + i][ax] = m.sbox_pos[i][ax] - e - 1e-6f; m.big_aabb[1 + i][3 + ax] = m.sbox_pos[i][ax] + e + 1e-6f;
+    }
+  for (int ax = 0; ax < 3; ++ax) {
+    float ext = ax == 1 ? 1e9f : m.belt_half[ax] + 1e-6f;
+    m.big_aabb[m.n_sbox + 1][ax] = m.belt_pos[ax] - ext; m.big_aabb[m.n_sbox + 1][3 + ax] = m.belt_pos[ax] + ext;
+  }
   const int32_t* cp = I(blob, n, "g_cluster_pair", &c);
-  m.n_cluster_pair = (int)(c / 2);
-  H.cpairs.resize(c);
-  for (size_t i = 0; i < c; ++i) H.cpairs[i] = (unsigned short)cp[i];
+  H.cpairs.clear();
+  for (size_t i = 0; i + 1 < c; i += 2) {
+    int c1 = cp[i], c2 = cp[i + 1];
+    int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2];
+    bool s1 = k1 == FM_CL_CUBE || k1 == FM_CL_ARM, s2 = k2 == FM_CL_CUBE || k2 == FM_CL_ARM;
+    unsigned type;
+    if (s1 && s2) type = FM_PAIR_SPH_SPH;
+    else if (s2 && k1 == FM_CL_PLANE) type = FM_PAIR_PLANE_SPH;
+    else if (s2) type = FM_PAIR_BOX_SPH;
+    else {   // two big geoms: only the belt moves, along its own long axis -> decided once
+      if (k1 == FM_CL_PLANE) { if (m.big_aabb[c2][2] > 0.f) continue; }
+      else {
+        bool sep = false;
+        for (int ax = 0; ax < 3; ++ax) sep = sep || m.big_aabb[c1][ax] > m.big_aabb[c2][3 + ax] || m.big_aabb[c2][ax] > m.big_aabb[c1][3 + ax];
+        if (sep) continue;
+      }
+      type = FM_PAIR_ALWAYS;
+    }
+    H.cpairs.push_back((unsigned)c1 | ((unsigned)c2 << 8) | (type << 16));
+  }
+  m.n_cluster_pair = (int)H.cpairs.size();
 }

@@ -17,7 +17,7 @@ struct DevRun {
 };
 
 template <int NA, int E>
-__global__ void __launch_bounds__(32 * E) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned short* __restrict__ cpairs,
+__global__ void __launch_bounds__(32 * E) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned int* __restrict__ cpairs,
                                                          const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvS<NA>* S = reinterpret_cast<EnvS<NA>*>(smem_raw);
@@ -43,7 +43,7 @@ __global__ void fm_ik_kernel(const FmIkModel* __restrict__ ik, FmEnvCfg cfg, FmS
 struct fm_handle {
   FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st;
   int E = 4; size_t smem = 0;
-  FmDevModel* d_model = nullptr; FmIkModel* d_ik = nullptr; unsigned short* d_cpairs = nullptr; int* d_geom_class = nullptr;
+  FmDevModel* d_model = nullptr; FmIkModel* d_ik = nullptr; unsigned int* d_cpairs = nullptr; int* d_geom_class = nullptr;
   FmDebugDump* d_dump = nullptr;
   long long launches = 0;
 };
@@ -88,8 +88,8 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_ik, sizeof(FmIkModel)));
     FM_CUDA(cudaMemcpy(h->d_ik, &h->hm.ik, sizeof(FmIkModel), cudaMemcpyHostToDevice));
-    FM_CUDA(cudaMalloc(&h->d_cpairs, h->hm.cpairs.size() * sizeof(unsigned short)));
-    FM_CUDA(cudaMemcpy(h->d_cpairs, h->hm.cpairs.data(), h->hm.cpairs.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMalloc(&h->d_cpairs, h->hm.cpairs.size() * sizeof(unsigned int)));
+    FM_CUDA(cudaMemcpy(h->d_cpairs, h->hm.cpairs.data(), h->hm.cpairs.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_geom_class, h->hm.geom_class.size() * sizeof(int)));
     FM_CUDA(cudaMemcpy(h->d_geom_class, h->hm.geom_class.data(), h->hm.geom_class.size() * sizeof(int), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_dump, sizeof(FmDebugDump)));

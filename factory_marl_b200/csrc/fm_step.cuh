@@ -33,6 +33,12 @@ static inline int fm_host_max(int* p, int v) { int o = *p; *p = o > v ? o : v; r
 #define FM_ATOMIC_MAXI(p, v) fm_host_max((p), (v))
 #endif
 
+#if !defined(__CUDACC__)
+static long long fm_dbg_sweeps = 0, fm_dbg_visits = 0, fm_dbg_islands = 0;   // host logic-test build only
+#define FM_DBG(x) x
+#else
+#define FM_DBG(x)
+#endif
 #define FM_QMAX 96
 #define FM_AROW 10   // equality + up to 9 limit rows per arm
 
@@ -47,34 +53,43 @@ struct EnvS {
   float cube_q[FM_NCUBE][7], cube_v[FM_NCUBE][6];
   float arm_q[NA][9], arm_v[NA][9];
   float ctrl_target[NU], ctrl[NU];
-  float acc_ws[NV];                         // qacc_warmstart: [0] belt, [1+6k] cube k, [61+9a] arm a
   float conveyor_speed;
   // ---- position-dependent (mj_step1)
-  float cube_R[FM_NCUBE][9], cube_x[FM_NCUBE][3];
-  float body_x[NA][FM_NARMBODY][3], body_R[NA][FM_NARMBODY][9], cl_x[NA][FM_NARMBODY][3];
+  int cube_sleep[FM_NCUBE];
+  float cube_R[FM_NCUBE][9], cube_x[FM_NCUBE][3], cube_vw[FM_NCUBE][6];   // cube_vw: (v, R*omega_local)
+  float body_x[NA][FM_NARMBODY][3], body_R[NA][FM_NARMBODY][9];
+  float bnd[FM_NCUBE + NA * FM_NARMBODY][4];   // bounding spheres (x, y, z, r) of the cube / arm-body clusters
   float M[NA][45], Minv[NA][81], Li[NA][45], Lc[NA][45];
   float bias[NA][9];
   // ---- acceleration stage
   float acc[NV];
   float belt_acc_smooth, belt_S;
+  float belt_part[NNODE];                   // per-island belt force partial sums (summed in fixed order: run-to-run determinism)
   // ---- arm-local rows (joint equality gripper.xml:46-49, joint limits)
   int arow_n[NA], arow_code[NA][FM_AROW];   // code: dof | sign<<8 (sign bit 1 = negative) ; 0x1000 = equality
   float arow_aref[NA][FM_AROW], arow_R[NA][FM_AROW], arow_f[NA][FM_AROW];
   // ---- contacts
   int ncon, nraw, n_armside, flags, nqueue;
-  int raw_key[FM_MAXCON], raw_g[FM_MAXCON];
-  float raw_d[FM_MAXCON][7];
   int c_side[FM_MAXCON], c_g[FM_MAXCON];
   float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_mu[FM_MAXCON], c_R[FM_MAXCON], c_W[FM_MAXCON][6];
   float c_aref[FM_MAXCON][4], c_f[FM_MAXCON][4];
   float as_J[FM_MAXARMSIDE][27], as_B[FM_MAXARMSIDE][27];
-  int isl_root[NNODE], isl_start[NNODE + 1];
-  unsigned char isl_list[FM_MAXCON];
+  int isl_root[NNODE], isl_start[NNODE + 1], need_union;
+  unsigned char isl_list[FM_MAXCON], c_node[FM_MAXCON];
   unsigned short queue[FM_QMAX];
-  // ---- per-body scratch of the arm recursions
-  float d_c[NA][FM_NARMBODY][3], d_Ic[NA][FM_NARMBODY][6], d_comp[NA][FM_NARMBODY][10];
-  float d_om[NA][FM_NARMBODY][3], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3];
-  float d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3];
+  // ---- per-body scratch of the arm recursions (dead after ph_arm_M) overlaid with the raw contact buffer (written by
+  //      ph_narrow, which the schedule runs after ph_arm_M, and dead after ph_contact_setup)
+  union {
+    struct {
+      float d_c[NA][FM_NARMBODY][3], d_Ic[NA][FM_NARMBODY][6], d_comp[NA][FM_NARMBODY][10];
+      float d_om[NA][FM_NARMBODY][3], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3];
+      float d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3];
+    };
+    struct {
+      int raw_key[FM_MAXCON], raw_g[FM_MAXCON];
+      float raw_d[FM_MAXCON][7];
+    };
+  };
   float force_max;
   // forces of the previous solve, keyed by contact identity (warm start of the dual; persisted in HBM between env steps)
   int prev_n, prev_key[FM_MAXCON];
@@ -96,6 +111,11 @@ FM_HD int pack_side(int type, int idx, int slot) { return type | (idx << 2) | (s
 FM_HD int side_type(int s) { return s & 3; }
 FM_HD int side_idx(int s) { return (s >> 2) & 127; }
 FM_HD int side_slot(int s) { return (s >> 9) & 15; }
+FM_HD int contact_node(int cs, int q) {   // island node of side q of a packed contact: cube k -> k, arm a -> 10 + a, else -1
+  int sd = (cs >> (13 * q)) & 8191;
+  int ty = side_type(sd), ix = side_idx(sd);
+  return ty == FM_SIDE_CUBE ? ix : (ty == FM_SIDE_ARM ? FM_NCUBE + (ix >> 4) : -1);
+}
 
 // parent of template body b (0 base .. 10 right plate)
 FM_HD int ab_parent(int b) { return b <= 8 ? b - 1 : 8; }
@@ -106,13 +126,28 @@ FM_HD int dof_body(int d) { return d < 7 ? d + 1 : d + 2; }
 // =====================================================================================================================
 // phase: cube kinematics (normalise quats in place as mj_kinematics does [3P])
 template <int NA, int E>
-FM_HD void ph_cube_derive(EnvS<NA>* S, int tid, int T) {
+FM_HD void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int sleep_hidden) {
   for (int w = tid; w < FM_NCUBE * E; w += T) {
     EnvS<NA>& s = S[w % E]; int k = w / E;
     q4 q = qnormf(mkq(s.cube_q[k][3], s.cube_q[k][4], s.cube_q[k][5], s.cube_q[k][6]));
     s.cube_q[k][3] = q.w; s.cube_q[k][4] = q.x; s.cube_q[k][5] = q.y; s.cube_q[k][6] = q.z;
     q2matf(q, s.cube_R[k]);
     s.cube_x[k][0] = s.cube_q[k][0]; s.cube_x[k][1] = s.cube_q[k][1]; s.cube_x[k][2] = s.cube_q[k][2];
+    // Hidden cubes (parked beyond the table at x = 4 / 5, task_utils.py:31,119) that have come to rest on the floor are put
+    // to sleep when cfg.sleep_hidden: no collision, no constraint rows, no integration, until the task manager moves them.
+    // They are invisible to observation and reward except through the velocity a cube keeps when it is spawned
+    // (SURVEY.md A.3), which this preserves to < 1e-5 m/s.
+    {
+      const float* vv = s.cube_v[k];
+      float v2 = vv[0] * vv[0] + vv[1] * vv[1] + vv[2] * vv[2], w2 = vv[3] * vv[3] + vv[4] * vv[4] + vv[5] * vv[5];
+      float hh = m.cube_half[k];
+      s.cube_sleep[k] = (sleep_hidden && s.cube_q[k][0] > 3.0f && s.cube_q[k][2] < hh * 1.01f && v2 < 1e-10f && w2 < 1e-7f) ? 1 : 0;
+    }
+    s.bnd[k][0] = s.cube_q[k][0]; s.bnd[k][1] = s.cube_q[k][1]; s.bnd[k][2] = s.cube_q[k][2];
+    s.bnd[k][3] = s.cube_sleep[k] ? -1.f : m.cube_half[k] * 1.7320509f * 1.000001f;
+    f3 ww = rmul(s.cube_R[k], mk3(s.cube_v[k][3], s.cube_v[k][4], s.cube_v[k][5]));
+    s.cube_vw[k][0] = s.cube_v[k][0]; s.cube_vw[k][1] = s.cube_v[k][1]; s.cube_vw[k][2] = s.cube_v[k][2];
+    s.cube_vw[k][3] = ww.x; s.cube_vw[k][4] = ww.y; s.cube_vw[k][5] = ww.z;
   }
 }
 
@@ -143,17 +178,16 @@ FM_HD void ph_arm_fk(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool with
         float sn, cs;
         sincosf(0.5f * s.arm_q[a][d], &sn, &cs);
         q = qmulf(q, mkq(cs, 0, 0, sn));
-        q = qnormf(q);
+        if (b == 4) q = qnormf(q);
         q2matf(q, R);
         if (with_vel) axv = rcol(R, 2) * s.arm_v[a][d];
       } else if (m.ab_jtype[b] == 2) {
-        q = qnormf(q);
         q2matf(q, R);
         f3 ax = rcol(R, 0);
         r = r + ax * s.arm_q[a][d];
         if (with_vel) axv = ax * s.arm_v[a][d];
       } else {
-        q = qnormf(q);
+        q = qnormf(q);      // gripper base: renormalise once before the plates branch off
         q2matf(q, R);
       }
       if (with_vel) {
@@ -177,7 +211,7 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
     const float* R = s.body_R[a][b];
-    st3(s.cl_x[a][b], ld3(s.body_x[a][b]) + rmul(R, ld3(m.arm_cl[b])));
+    { f3 cc = ld3(s.body_x[a][b]) + rmul(R, ld3(m.arm_cl[b])); float* bb = s.bnd[FM_NCUBE + ab]; bb[0] = cc.x; bb[1] = cc.y; bb[2] = cc.z; bb[3] = m.arm_cl[b][3]; }
     if (b == 0) continue;
     float ms = m.ab_mass[b];
     f3 c = rmul(R, ld3(m.ab_ipos[b]));
@@ -277,27 +311,44 @@ FM_HD void ph_arm_chol(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   for (int w = tid; w < 2 * NA * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ai = w / E; int a = ai >> 1, which = ai & 1;
     float L[45];
+#pragma unroll
     for (int i = 0; i < 45; ++i) L[i] = s.M[a][i];
     if (which) {
       for (int d = 0; d < 7; ++d) L[tri(d, d)] += m.h * m.kd;
       float gd = m.h * m.g_kd;   // gripper tendon actuator: moment^T * kd * moment (never force-clamped in range)
       L[tri(7, 7)] += gd * m.ten0 * m.ten0; L[tri(8, 8)] += gd * m.ten1 * m.ten1; L[tri(8, 7)] += gd * m.ten0 * m.ten1;
     }
+#pragma unroll
     for (int i = 0; i < 9; ++i)
+#pragma unroll
       for (int j = 0; j <= i; ++j) {
         float sum = L[tri(i, j)];
+#pragma unroll
         for (int k = 0; k < j; ++k) sum -= L[tri(i, k)] * L[tri(j, k)];
         if (i == j) L[tri(i, i)] = sqrtf(fmaxf(sum, 1e-20f));
         else L[tri(i, j)] = sum / L[tri(j, j)];
       }
     float* out = which ? s.Li[a] : s.Lc[a];
+#pragma unroll
     for (int i = 0; i < 45; ++i) out[i] = L[i];
   }
 }
 
 FM_HD void chol9_solve(const float* L, float* x) {
-  for (int i = 0; i < 9; ++i) { float sum = x[i]; for (int k = 0; k < i; ++k) sum -= L[tri(i, k)] * x[k]; x[i] = sum / L[tri(i, i)]; }
-  for (int i = 8; i >= 0; --i) { float sum = x[i]; for (int k = i + 1; k < 9; ++k) sum -= L[tri(k, i)] * x[k]; x[i] = sum / L[tri(i, i)]; }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    float sum = x[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) sum -= L[tri(i, k)] * x[k];
+    x[i] = sum / L[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 8; i >= 0; --i) {
+    float sum = x[i];
+#pragma unroll
+    for (int k = i + 1; k < 9; ++k) sum -= L[tri(k, i)] * x[k];
+    x[i] = sum / L[tri(i, i)];
+  }
 }
 
 // phase: explicit inverse, one column per thread
@@ -306,20 +357,17 @@ FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
   for (int w = tid; w < NA * 9 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ac = w / E; int a = ac / 9, c = ac % 9;
     float x[9];
+#pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = i == c ? 1.f : 0.f;
     chol9_solve(s.Lc[a], x);
+#pragma unroll
     for (int i = 0; i < 9; ++i) s.Minv[a][9 * i + c] = x[i];
   }
 }
 
 // =====================================================================================================================
-// broad phase: one cluster pair per work item; survivors are queued for the narrow phase
-template <int NA>
-FM_HD bool cluster_sphere(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, f3& c, float& r) {
-  if (kind == FM_CL_CUBE) { c = ld3(s.cube_x[idx]); r = m.cube_half[idx] * 1.7320509f; return true; }
-  if (kind == FM_CL_ARM) { int a = idx / FM_NARMBODY, b = idx % FM_NARMBODY; c = ld3(s.cl_x[a][b]); r = m.arm_cl[b][3]; return true; }
-  return false;
-}
+// broad phase: one cluster pair per work item; survivors are queued for the narrow phase.  Every moving cluster has a
+// bounding sphere in shared memory; big geoms (floor, static boxes, belt) have conservative world AABBs in the model.
 template <int NA>
 FM_HD void cluster_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, f3& p, const float*& R, f3& hs, float* Rid) {
   if (kind == FM_CL_SBOX) { p = ld3(m.sbox_pos[idx]); R = m.sbox_R[idx]; hs = ld3(m.sbox_half[idx]); }
@@ -330,26 +378,26 @@ FM_HD void cluster_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx
 }
 
 template <int NA, int E>
-FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned short* __restrict__ cpairs, int tid, int T) {
-  int np = m.n_cluster_pair;
+FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
+  const int np = m.n_cluster_pair, s0 = m.cl_sph0;
   for (int w = tid; w < np * E; w += T) {
     EnvS<NA>& s = S[w % E]; int pi = w / E;
-    int c1 = cpairs[2 * pi], c2 = cpairs[2 * pi + 1];
-    int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2], i1 = m.cl_idx[c1], i2 = m.cl_idx[c2];
-    f3 ca, cb; float ra, rb;
-    bool sa = cluster_sphere(s, m, k1, i1, ca, ra), sb = cluster_sphere(s, m, k2, i2, cb, rb);
-    bool far = false;
-    if (sa && sb) { f3 d = ca - cb; float rr = ra + rb; far = dot3(d, d) > rr * rr; }
-    else if (sa || sb) {
-      f3 c = sa ? ca : cb; float r = sa ? ra : rb; int ko = sa ? k2 : k1, io = sa ? i2 : i1;
-      if (ko == FM_CL_PLANE) far = c.z - r > 0.f;
-      else { f3 p, hs; const float* R; float Rid[9]; cluster_box(s, m, ko, io, p, R, hs, Rid); far = far_sphere_box(c, r, p, R, hs); }
-    }
-    else {   // two big geoms (floor / static box / belt): only the belt moves, along its own long axis
-      if (k1 == FM_CL_PLANE) far = k2 != FM_CL_BELT || m.belt_pos[2] - m.belt_half[2] > 0.f;
-      else if (k2 == FM_CL_BELT) { f3 p, hs; const float* R; float Rid[9]; cluster_box(s, m, k2, i2, p, R, hs, Rid); far = far_sphere_box(ld3(m.sbox_pos[i1]), norm3(ld3(m.sbox_half[i1])), p, R, hs); }
-      else far = true;
-    }
+    unsigned rec = cpairs[pi];
+    int c1 = rec & 255, c2 = (rec >> 8) & 255, type = rec >> 16;
+    const float* b2 = s.bnd[c2 - s0];
+    bool far;
+    if (b2[3] < 0.f) far = true;                       // sleeping cube
+    else if (type == FM_PAIR_SPH_SPH) {
+      const float* b1 = s.bnd[c1 - s0];
+      if (b1[3] < 0.f) continue;
+      float dx = b1[0] - b2[0], dy = b1[1] - b2[1], dz = b1[2] - b2[2], rr = b1[3] + b2[3];
+      far = dx * dx + dy * dy + dz * dz > rr * rr;
+    } else if (type == FM_PAIR_BOX_SPH) {
+      const float* bx = m.big_aabb[c1];
+      float dx = fmaxf(fmaxf(bx[0] - b2[0], b2[0] - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - b2[1], b2[1] - bx[4]), 0.f), dz = fmaxf(fmaxf(bx[2] - b2[2], b2[2] - bx[5]), 0.f);
+      far = dx * dx + dy * dy + dz * dz > b2[3] * b2[3];
+    } else if (type == FM_PAIR_PLANE_SPH) far = b2[2] - b2[3] > 0.f;
+    else far = false;
     if (far) continue;
     int slot = FM_ATOMIC_ADD(&s.nqueue, 1);
     if (slot < FM_QMAX) s.queue[slot] = (unsigned short)pi; else FM_ATOMIC_OR(&s.flags, FM_FLAG_QUEUE_OVERFLOW);
@@ -394,61 +442,69 @@ FM_HD void pair_box_box(EnvS<NA>& s, const GeomBox& x, const GeomBox& y, bool ar
   emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rc, n);
 }
 
+// Narrow phase.  Work item = (queued cluster pair, sub-index j): when the second cluster is an arm body, j selects ONE of
+// its geoms (spheres first, then boxes) which is tested against the whole first cluster; otherwise only j == 0 does work.
+// This bounds the longest serial chain of the phase by one body's geom count instead of the product of two.
+#define FM_NSUB 13
+template <int NA>
+FM_HD void narrow_arm_geom_vs(EnvS<NA>& s, const FmDevModel& m, int a2, int b2, int j, int k1, int i1) {
+  RawC rc[8]; float RidA[9], RidB[9];
+  int s0 = m.body_sph_start[b2], ns = m.body_sph_start[b2 + 1] - s0, x0 = m.body_box_start[b2], nb = m.body_box_start[b2 + 1] - x0;
+  if (j >= ns + nb) return;
+  bool is_sph = j < ns;
+  int side2 = b2 == 0 ? pack_side(FM_SIDE_STATIC, 0, 0) : pack_side(FM_SIDE_ARM, a2 * 16 + b2, 0);
+  const float* R2 = s.body_R[a2][b2]; f3 p2 = ld3(s.body_x[a2][b2]);
+  f3 sq = mk3(0, 0, 0); float sr = 0.f; int sg = 0; GeomBox g2;
+  if (is_sph) { int si = s0 + j; sq = p2 + rmul(R2, ld3(m.sph_pos[si])); sr = m.sph_r[si]; sg = m.arm_first_geom[a2] + m.sph_geom[si]; }
+  else get_box(s, m, FM_CL_ARM, a2 * FM_NARMBODY + b2, x0 + (j - ns), g2, RidB);
+  if (k1 == FM_CL_PLANE) {
+    if (is_sph) { int n = col_plane_sphere(sq, sr, rc); emit(s, 0, sg, pack_side(FM_SIDE_STATIC, 0, 0), side2, true, rc, n); }
+    else { int n = col_plane_box(g2.p, g2.R, g2.hs, rc); emit(s, 0, g2.geom, pack_side(FM_SIDE_STATIC, 0, 0), g2.side, true, rc, n); }
+  } else if (k1 != FM_CL_ARM) {     // static box / belt / cube
+    GeomBox x; get_box(s, m, k1, i1, 0, x, RidA);
+    if (is_sph) { int n = col_sphere_box(sq, sr, x.p, x.R, x.hs, rc); emit(s, sg, x.geom, side2, x.side, true, rc, n); }   // sphere is geom1 (lower type) [3P]
+    else pair_box_box(s, x, g2, true);
+  } else {                          // arm body vs arm body
+    int a1 = i1 / FM_NARMBODY, b1 = i1 % FM_NARMBODY;
+    int t0 = m.body_sph_start[b1], t1 = m.body_sph_start[b1 + 1], y0 = m.body_box_start[b1], y1 = m.body_box_start[b1 + 1];
+    int side1 = b1 == 0 ? pack_side(FM_SIDE_STATIC, 0, 0) : pack_side(FM_SIDE_ARM, a1 * 16 + b1, 0);
+    const float* R1 = s.body_R[a1][b1]; f3 p1 = ld3(s.body_x[a1][b1]);
+    for (int si = t0; si < t1; ++si) {
+      f3 sp = p1 + rmul(R1, ld3(m.sph_pos[si])); float r1 = m.sph_r[si]; int g1 = m.arm_first_geom[a1] + m.sph_geom[si];
+      if (is_sph) {
+        if (g1 < sg) { int n = col_sphere_sphere(sp, r1, sq, sr, rc); emit(s, g1, sg, side1, side2, true, rc, n); }
+        else { int n = col_sphere_sphere(sq, sr, sp, r1, rc); emit(s, sg, g1, side2, side1, true, rc, n); }
+      } else { int n = col_sphere_box(sp, r1, g2.p, g2.R, g2.hs, rc); emit(s, g1, g2.geom, side1, g2.side, true, rc, n); }
+    }
+    for (int bi = y0; bi < y1; ++bi) {
+      GeomBox g1; get_box(s, m, k1, i1, bi, g1, RidA);
+      if (is_sph) { int n = col_sphere_box(sq, sr, g1.p, g1.R, g1.hs, rc); emit(s, sg, g1.geom, side2, g1.side, true, rc, n); }
+      else pair_box_box(s, g1, g2, true);
+    }
+  }
+}
+
 template <int NA, int E>
-FM_HD void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned short* __restrict__ cpairs, int tid, int T) {
-  for (int w = tid; w < FM_QMAX * E; w += T) {
-    EnvS<NA>& s = S[w % E]; int qi = w / E;
+FM_HD void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
+  int mq = 0;
+  for (int e = 0; e < E; ++e) mq = S[e].nqueue > mq ? S[e].nqueue : mq;
+  if (mq > FM_QMAX) mq = FM_QMAX;
+  for (int w = tid; w < mq * FM_NSUB * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int rest = w / E; int qi = rest / FM_NSUB, j = rest % FM_NSUB;
     int nq = s.nqueue < FM_QMAX ? s.nqueue : FM_QMAX;
     if (qi >= nq) continue;
-    int pi = s.queue[qi];
-    int c1 = cpairs[2 * pi], c2 = cpairs[2 * pi + 1];
+    unsigned rec = cpairs[s.queue[qi]];
+    int c1 = rec & 255, c2 = (rec >> 8) & 255;
     int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2], i1 = m.cl_idx[c1], i2 = m.cl_idx[c2];
+    if (k2 == FM_CL_ARM) { narrow_arm_geom_vs(s, m, i2 / FM_NARMBODY, i2 % FM_NARMBODY, j, k1, i1); continue; }
+    if (j != 0) continue;
     RawC rc[8]; float RidA[9], RidB[9];
-    if (k2 != FM_CL_ARM) {
-      // no arm involved: plane/sbox/belt/cube vs belt/cube
-      if (k1 == FM_CL_PLANE) {
-        if (k2 == FM_CL_CUBE) { float h = m.cube_half[i2]; int n = col_plane_box(ld3(s.cube_x[i2]), s.cube_R[i2], mk3(h, h, h), rc); emit(s, 0, m.cube_geom[i2], pack_side(FM_SIDE_STATIC, 0, 0), pack_side(FM_SIDE_CUBE, i2, 0), false, rc, n); }
-        else if (k2 == FM_CL_BELT) { GeomBox b; get_box(s, m, k2, i2, 0, b, RidB); int n = col_plane_box(b.p, b.R, b.hs, rc); emit(s, 0, b.geom, pack_side(FM_SIDE_STATIC, 0, 0), b.side, false, rc, n); }
-      } else {
-        GeomBox x, y; get_box(s, m, k1, i1, 0, x, RidA); get_box(s, m, k2, i2, 0, y, RidB);
-        pair_box_box(s, x, y, false);
-      }
-      continue;
-    }
-    // second cluster is an arm body
-    int a2 = i2 / FM_NARMBODY, b2 = i2 % FM_NARMBODY;
-    int s0 = m.body_sph_start[b2], s1 = m.body_sph_start[b2 + 1], x0 = m.body_box_start[b2], x1 = m.body_box_start[b2 + 1];
-    int side2 = b2 == 0 ? pack_side(FM_SIDE_STATIC, 0, 0) : pack_side(FM_SIDE_ARM, a2 * 16 + b2, 0);
-    const float* R2 = s.body_R[a2][b2]; f3 p2 = ld3(s.body_x[a2][b2]);
     if (k1 == FM_CL_PLANE) {
-      for (int si = s0; si < s1; ++si) { int n = col_plane_sphere(p2 + rmul(R2, ld3(m.sph_pos[si])), m.sph_r[si], rc); emit(s, 0, m.arm_first_geom[a2] + m.sph_geom[si], pack_side(FM_SIDE_STATIC, 0, 0), side2, true, rc, n); }
-      for (int bi = x0; bi < x1; ++bi) { GeomBox g; get_box(s, m, k2, i2, bi, g, RidB); int n = col_plane_box(g.p, g.R, g.hs, rc); emit(s, 0, g.geom, pack_side(FM_SIDE_STATIC, 0, 0), g.side, true, rc, n); }
-    } else if (k1 != FM_CL_ARM) {   // static box / belt / cube  vs  arm body
-      GeomBox x; get_box(s, m, k1, i1, 0, x, RidA);
-      for (int si = s0; si < s1; ++si) {
-        int n = col_sphere_box(p2 + rmul(R2, ld3(m.sph_pos[si])), m.sph_r[si], x.p, x.R, x.hs, rc);
-        emit(s, m.arm_first_geom[a2] + m.sph_geom[si], x.geom, side2, x.side, true, rc, n);     // sphere is geom1 (lower type) [3P]
-      }
-      for (int bi = x0; bi < x1; ++bi) { GeomBox g; get_box(s, m, k2, i2, bi, g, RidB); pair_box_box(s, x, g, true); }
-    } else {                        // arm body vs arm body
-      int a1 = i1 / FM_NARMBODY, b1 = i1 % FM_NARMBODY;
-      int t0 = m.body_sph_start[b1], t1 = m.body_sph_start[b1 + 1], y0 = m.body_box_start[b1], y1 = m.body_box_start[b1 + 1];
-      int side1 = b1 == 0 ? pack_side(FM_SIDE_STATIC, 0, 0) : pack_side(FM_SIDE_ARM, a1 * 16 + b1, 0);
-      const float* R1 = s.body_R[a1][b1]; f3 p1 = ld3(s.body_x[a1][b1]);
-      for (int si = t0; si < t1; ++si) {
-        f3 sp = p1 + rmul(R1, ld3(m.sph_pos[si])); float sr = m.sph_r[si]; int sg = m.arm_first_geom[a1] + m.sph_geom[si];
-        for (int sj = s0; sj < s1; ++sj) {
-          f3 sq = p2 + rmul(R2, ld3(m.sph_pos[sj])); int gj = m.arm_first_geom[a2] + m.sph_geom[sj];
-          if (sg < gj) { int n = col_sphere_sphere(sp, sr, sq, m.sph_r[sj], rc); emit(s, sg, gj, side1, side2, true, rc, n); }
-          else { int n = col_sphere_sphere(sq, m.sph_r[sj], sp, sr, rc); emit(s, gj, sg, side2, side1, true, rc, n); }
-        }
-        for (int bj = x0; bj < x1; ++bj) { GeomBox g; get_box(s, m, k2, i2, bj, g, RidB); int n = col_sphere_box(sp, sr, g.p, g.R, g.hs, rc); emit(s, sg, g.geom, side1, g.side, true, rc, n); }
-      }
-      for (int bi = y0; bi < y1; ++bi) {
-        GeomBox g1; get_box(s, m, k1, i1, bi, g1, RidA);
-        for (int sj = s0; sj < s1; ++sj) { f3 sq = p2 + rmul(R2, ld3(m.sph_pos[sj])); int n = col_sphere_box(sq, m.sph_r[sj], g1.p, g1.R, g1.hs, rc); emit(s, m.arm_first_geom[a2] + m.sph_geom[sj], g1.geom, side2, g1.side, true, rc, n); }
-        for (int bj = x0; bj < x1; ++bj) { GeomBox g2; get_box(s, m, k2, i2, bj, g2, RidB); pair_box_box(s, g1, g2, true); }
-      }
+      if (k2 == FM_CL_CUBE) { float h = m.cube_half[i2]; int n = col_plane_box(ld3(s.cube_x[i2]), s.cube_R[i2], mk3(h, h, h), rc); emit(s, 0, m.cube_geom[i2], pack_side(FM_SIDE_STATIC, 0, 0), pack_side(FM_SIDE_CUBE, i2, 0), false, rc, n); }
+      else if (k2 == FM_CL_BELT) { GeomBox b; get_box(s, m, k2, i2, 0, b, RidB); int n = col_plane_box(b.p, b.R, b.hs, rc); emit(s, 0, b.geom, pack_side(FM_SIDE_STATIC, 0, 0), b.side, false, rc, n); }
+    } else {
+      GeomBox x, y; get_box(s, m, k1, i1, 0, x, RidA); get_box(s, m, k2, i2, 0, y, RidB);
+      pair_box_box(s, x, y, false);
     }
   }
 }
@@ -464,6 +520,7 @@ FM_HD void impedance_f(const float* solref, const float* solimp, float pos, floa
     if (x >= 1.f) y = 1.f;
     else if (x <= 0.f) y = 0.f;
     else if (power == 1.f) y = x;
+    else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
     else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
     else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
     imp = dmin + y * (dmax - dmin);
@@ -473,11 +530,13 @@ FM_HD void impedance_f(const float* solref, const float* solimp, float pos, floa
   B = 2.f / fmaxf(1e-15f, dmax * tc);
 }
 
-// per-side working set of a contact (contact-space Jacobian base rows n, t1, t2)
+// per-side working set of a contact (contact-space Jacobian base rows n, t1, t2).
+// Cubes have isotropic inertia (uniform box with equal sides, scene.py:9-23), so their angular acceleration is kept in the
+// WORLD frame during the solve: J a = d . (a_lin + alpha x r) and Minv J^T lam = (F/m, (r x F)/I) with F = sum_q d_q lam_q.
 struct SideW {
   int type, idx;
   float sgn;
-  f3 ja[3];            // cube: angular rows (body-local)
+  f3 r;                // cube: contact point relative to the cube centre
   float invm, invI;
   float jb[3];         // belt: scalar rows
   const float* J; const float* B;   // arm: 3x9 each
@@ -488,8 +547,7 @@ FM_HD void side_prepare(const EnvS<NA>& s, const FmDevModel& m, int sd, float sg
   o.type = side_type(sd); o.idx = side_idx(sd); o.sgn = sgn;
   if (o.type == FM_SIDE_CUBE) {
     int k = o.idx;
-    f3 r = p - ld3(s.cube_x[k]);
-    o.ja[0] = rmulT(s.cube_R[k], cross3(r, n)); o.ja[1] = rmulT(s.cube_R[k], cross3(r, t1)); o.ja[2] = rmulT(s.cube_R[k], cross3(r, t2));
+    o.r = p - ld3(s.cube_x[k]);
     o.invm = 1.0f / m.cube_mass[k]; o.invI = 1.0f / m.cube_inertia[k];
   } else if (o.type == FM_SIDE_BELT) {
     o.jb[0] = n.y; o.jb[1] = t1.y; o.jb[2] = t2.y;
@@ -498,13 +556,13 @@ FM_HD void side_prepare(const EnvS<NA>& s, const FmDevModel& m, int sd, float sg
     o.J = s.as_J[sl]; o.B = s.as_B[sl];
   }
 }
-// u += sgn * Jbase * vec  (vec: per-block generalized vector)
+// u += sgn * Jbase * vec ; cube block of `cube` = [linear(3), angular(3) in the WORLD frame]
 template <int NA>
 FM_HD void side_dot(const SideW& o, f3 n, f3 t1, f3 t2, const float* belt, const float* cube, const float* arm, float* u) {
   if (o.type == FM_SIDE_CUBE) {
     const float* v = cube + 6 * o.idx;
-    f3 vl = mk3(v[0], v[1], v[2]), va = mk3(v[3], v[4], v[5]);
-    u[0] += o.sgn * (dot3(n, vl) + dot3(o.ja[0], va)); u[1] += o.sgn * (dot3(t1, vl) + dot3(o.ja[1], va)); u[2] += o.sgn * (dot3(t2, vl) + dot3(o.ja[2], va));
+    f3 pv = mk3(v[0], v[1], v[2]) + cross3(mk3(v[3], v[4], v[5]), o.r);
+    u[0] += o.sgn * dot3(n, pv); u[1] += o.sgn * dot3(t1, pv); u[2] += o.sgn * dot3(t2, pv);
   } else if (o.type == FM_SIDE_BELT) {
     float v = belt[0];
     u[0] += o.sgn * o.jb[0] * v; u[1] += o.sgn * o.jb[1] * v; u[2] += o.sgn * o.jb[2] * v;
@@ -518,8 +576,8 @@ template <int NA>
 FM_HD void side_apply(const SideW& o, f3 n, f3 t1, f3 t2, float* cube, float* arm, const float* lam) {
   if (o.type == FM_SIDE_CUBE) {
     float* v = cube + 6 * o.idx;
-    f3 fl = (n * lam[0] + t1 * lam[1] + t2 * lam[2]) * (o.sgn * o.invm);
-    f3 fa = (o.ja[0] * lam[0] + o.ja[1] * lam[1] + o.ja[2] * lam[2]) * (o.sgn * o.invI);
+    f3 F = (n * lam[0] + t1 * lam[1] + t2 * lam[2]) * o.sgn;
+    f3 fl = F * o.invm, fa = cross3(o.r, F) * o.invI;
     v[0] += fl.x; v[1] += fl.y; v[2] += fl.z; v[3] += fa.x; v[4] += fa.y; v[5] += fa.z;
   } else if (o.type == FM_SIDE_ARM) {
     float* v = arm + 9 * (o.idx >> 4);
@@ -534,8 +592,15 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
     int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
     if (ri >= nraw) continue;
     int key = s.raw_key[ri];
-    int rank = 0;
-    for (int k = 0; k < nraw; ++k) rank += (s.raw_key[k] < key) ? 1 : 0;
+    // rank = sorted position; arm-side slots are handed out in the same order (deterministic, independent of atomics)
+    int rank = 0, slot_base = 0;
+    for (int k = 0; k < nraw; ++k) {
+      if (s.raw_key[k] < key) {
+        rank++;
+        int g = s.raw_g[k];
+        slot_base += (side_type(g & 8191) == FM_SIDE_ARM ? 1 : 0) + (side_type((g >> 13) & 8191) == FM_SIDE_ARM ? 1 : 0);
+      }
+    }
     int c = rank;
     int g1 = key >> 13, g2 = (key >> 4) & 511;
     int rg = s.raw_g[ri];
@@ -556,7 +621,7 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
       else if (ty == FM_SIDE_ARM) {
         int a = ix >> 4, b = ix & 15;
         invw += m.ab_invw[b];
-        int sl = FM_ATOMIC_ADD(&s.n_armside, 1);
+        int sl = slot_base++;
         if (sl >= FM_MAXARMSIDE) { FM_ATOMIC_OR(&s.flags, FM_FLAG_ARMSIDE_OVERFLOW); sds[sdi] = pack_side(FM_SIDE_STATIC, 0, 0); continue; }
         sds[sdi] = pack_side(ty, ix, sl);
         float* J = s.as_J[sl]; float* Bv = s.as_B[sl];
@@ -573,6 +638,12 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
       }
     }
     s.c_side[c] = sds[0] | (sds[1] << 13) | (armgeom ? (1 << 30) : 0);
+    {
+      int cs2 = s.c_side[c];
+      int n0 = contact_node(cs2, 0), n1 = contact_node(cs2, 1);
+      s.c_node[c] = (unsigned char)(n0 >= 0 ? n0 : (n1 >= 0 ? n1 : 255));
+      if (n0 >= 0 && n1 >= 0 && n0 != n1) s.need_union = 1;
+    }
     s.c_g[c] = (g1 << 12) | g2;
     st3(s.c_p[c], p); st3(s.c_n[c], n); s.c_mu[c] = mu;
     float K, Bd, imp; impedance_f(pp + 1, pp + 3, dist, m.h, K, Bd, imp);
@@ -589,8 +660,9 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
     for (int q = 0; q < 2; ++q) {
       const SideW& o = *sw[q];
       if (o.type == FM_SIDE_CUBE) {
-        W[0] += o.invm + o.invI * dot3(o.ja[0], o.ja[0]); W[1] += o.invm + o.invI * dot3(o.ja[1], o.ja[1]); W[2] += o.invm + o.invI * dot3(o.ja[2], o.ja[2]);
-        W[3] += o.invI * dot3(o.ja[0], o.ja[1]); W[4] += o.invI * dot3(o.ja[0], o.ja[2]); W[5] += o.invI * dot3(o.ja[1], o.ja[2]);
+        f3 a0 = cross3(o.r, n), a1 = cross3(o.r, t1), a2 = cross3(o.r, t2);
+        W[0] += o.invm + o.invI * dot3(a0, a0); W[1] += o.invm + o.invI * dot3(a1, a1); W[2] += o.invm + o.invI * dot3(a2, a2);
+        W[3] += o.invI * dot3(a0, a1); W[4] += o.invI * dot3(a0, a2); W[5] += o.invI * dot3(a1, a2);
       } else if (o.type == FM_SIDE_BELT) {
         float im = 1.0f / m.belt_mass;
         W[0] += im * o.jb[0] * o.jb[0]; W[1] += im * o.jb[1] * o.jb[1]; W[2] += im * o.jb[2] * o.jb[2];
@@ -606,16 +678,15 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
     }
     for (int q = 0; q < 6; ++q) s.c_W[c][q] = W[q];
     // velocity and warm-start acceleration in contact space
-    float uv[3] = {0, 0, 0}, ua[3] = {0, 0, 0};
-    side_dot<NA>(A, n, t1, t2, &s.belt_v, &s.cube_v[0][0], &s.arm_v[0][0], uv);
-    side_dot<NA>(Bs, n, t1, t2, &s.belt_v, &s.cube_v[0][0], &s.arm_v[0][0], uv);
+    float uv[3] = {0, 0, 0};
+    side_dot<NA>(A, n, t1, t2, &s.belt_v, &s.cube_vw[0][0], &s.arm_v[0][0], uv);
+    side_dot<NA>(Bs, n, t1, t2, &s.belt_v, &s.cube_vw[0][0], &s.arm_v[0][0], uv);
     float kid = K * imp * dist;
     for (int r = 0; r < 4; ++r) {
       int tq = 1 + (r >> 1); float cf = (r & 1) ? -mu : mu;
       float vel = uv[0] + cf * uv[tq];
       float aref = -Bd * vel - kid;
       s.c_aref[c][r] = aref;
-      (void)ua;
     }
     // warm start: forces of the previous solve for the same contact (geom pair + index); binary search on sorted keys.
     // (MuJoCo warm-starts the dual from qacc_warmstart as f = -jar/R; in fp32 that quotient is dominated by rounding.)
@@ -667,39 +738,50 @@ FM_HD void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 }
 
 // phase: constraint islands (thread per env): union-find over cubes and arms, contact lists per island root
+// Constraint islands.  Nodes = cubes and arms; a contact belongs to the island of its dynamic side(s).  Almost always no
+// contact couples two dynamic nodes (cube-cube, cube-arm, arm-arm), so every node is its own island and the per-island
+// contact lists are built fully in parallel (ph_island_lists).  Otherwise one thread per env runs a union-find first.
 template <int NA, int E>
-FM_HD void ph_islands(EnvS<NA>* S, int tid, int T) {
+FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
     int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
     s.ncon = nraw;
-    int root[NN];
-    for (int i = 0; i < NN; ++i) root[i] = i;
-    int node_of[FM_MAXCON];
+    if (!s.need_union) continue;
+    int* root = s.isl_root;
     for (int c = 0; c < nraw; ++c) {
       int cs = s.c_side[c];
-      int nd[2] = {-1, -1};
-      for (int q = 0; q < 2; ++q) {
-        int sd = (cs >> (13 * q)) & 8191;
-        int ty = side_type(sd), ix = side_idx(sd);
-        if (ty == FM_SIDE_CUBE) nd[q] = ix; else if (ty == FM_SIDE_ARM) nd[q] = FM_NCUBE + (ix >> 4);
-      }
-      int x = nd[0] >= 0 ? nd[0] : nd[1];
-      node_of[c] = x;
-      if (nd[0] >= 0 && nd[1] >= 0) {
-        int ra = nd[0]; while (root[ra] != ra) ra = root[ra];
-        int rb = nd[1]; while (root[rb] != rb) rb = root[rb];
+      int n0 = contact_node(cs, 0), n1 = contact_node(cs, 1);
+      if (n0 >= 0 && n1 >= 0) {
+        int ra = n0; while (root[ra] != ra) ra = root[ra];
+        int rb = n1; while (root[rb] != rb) rb = root[rb];
         if (ra != rb) { if (ra < rb) root[rb] = ra; else root[ra] = rb; }
       }
     }
-    for (int i = 0; i < NN; ++i) { int r = i; while (root[r] != r) r = root[r]; root[i] = r; s.isl_root[i] = r; }
-    int cnt[NN + 1];
-    for (int i = 0; i <= NN; ++i) cnt[i] = 0;
-    for (int c = 0; c < nraw; ++c) if (node_of[c] >= 0) cnt[root[node_of[c]] + 1]++;
-    for (int i = 0; i < NN; ++i) cnt[i + 1] += cnt[i];
-    for (int i = 0; i <= NN; ++i) s.isl_start[i] = cnt[i];
-    for (int c = 0; c < nraw; ++c) if (node_of[c] >= 0) { int r = root[node_of[c]]; s.isl_list[cnt[r]++] = (unsigned char)c; }
+    for (int i = 0; i < NN; ++i) { int r = i; while (root[r] != r) r = root[r]; root[i] = r; }
+  }
+}
+template <int NA, int E>
+FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
+  const int NN = EnvS<NA>::NNODE;
+  for (int w = tid; w < (FM_MAXCON + NN + 1) * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int i = w / E;
+    int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
+    if (i < FM_MAXCON) {
+      if (i >= nraw) continue;
+      int nd = s.c_node[i];
+      if (nd == 255) continue;
+      int r = s.isl_root[nd];
+      int pos = 0;
+      for (int c = 0; c < nraw; ++c) { int n2 = s.c_node[c]; if (n2 == 255) continue; int r2 = s.isl_root[n2]; pos += (r2 < r || (r2 == r && c < i)) ? 1 : 0; }
+      s.isl_list[pos] = (unsigned char)i;
+    } else {
+      int node = i - FM_MAXCON;      // 0..NN: start offset of island `node` (NN = end sentinel)
+      int cnt = 0;
+      for (int c = 0; c < nraw; ++c) { int n2 = s.c_node[c]; if (n2 == 255) continue; cnt += (s.isl_root[n2] < node) ? 1 : 0; }
+      s.isl_start[node] = cnt;
+    }
   }
 }
 
@@ -712,7 +794,7 @@ FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
     if (i == 0) {
       float c = clampf(s.ctrl_target[0], m.ctrl_lo[0], m.ctrl_hi[0]);
       float f = m.belt_kv * (c - s.belt_v) - m.belt_damp * s.belt_v;
-      s.belt_acc_smooth = f / m.belt_mass; s.acc[0] = s.belt_acc_smooth; s.belt_S = 0.f;
+      s.belt_acc_smooth = f / m.belt_mass; s.acc[0] = s.belt_acc_smooth + s.belt_S;
     } else if (i <= FM_NCUBE) {
       float* a = &s.acc[1 + 6 * (i - 1)];
       a[0] = 0; a[1] = 0; a[2] = -m.g; a[3] = 0; a[4] = 0; a[5] = 0;
@@ -808,36 +890,42 @@ FM_HD float arm_rows_visit(EnvS<NA>& s, int a, bool first) {
 }
 
 template <int NA, int E>
-FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool first_outer, int inner, float tol) {
+FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < NN * E; w += T) {
     EnvS<NA>& s = S[w % E]; int node = w / E;
+    s.belt_part[node] = 0.f;
     if (s.isl_root[node] != node) continue;
     int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
     bool has_arm = false;
     for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
     if (c0 == c1 && !has_arm) continue;
     float belt_sum = 0.f;
-    if (first_outer) {
-      for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) arm_rows_visit(s, a, true);
-      for (int ci = c0; ci < c1; ++ci) contact_visit(s, m, s.isl_list[ci], true, belt_sum);
-    }
+    // warm start: apply the previous solve's forces
+    for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) arm_rows_visit(s, a, true);
+    for (int ci = c0; ci < c1; ++ci) contact_visit(s, m, s.isl_list[ci], true, belt_sum);
+    FM_DBG(fm_dbg_islands++;)
     for (int it = 0; it < inner; ++it) {
       float maxd = 0.f; belt_sum = 0.f;
+      FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0;)
       for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, false));
       for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, contact_visit(s, m, s.isl_list[ci], false, belt_sum));
       if (maxd < tol) break;
     }
-    if (belt_sum != 0.f) FM_ATOMIC_ADDF(&s.belt_S, belt_sum);
+    s.belt_part[node] = belt_sum;
   }
 }
 
+// belt acceleration from this solve's contact forces (fixed summation order: run-to-run determinism).  During the solve the
+// belt dof is held at its smooth acceleration plus the previous sub-step's contact term (the coupling is ~1e-3 of a cube's).
 template <int NA, int E>
 FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
-    s.acc[0] = s.belt_acc_smooth + s.belt_S / m.belt_mass;
-    s.belt_S = 0.f;
+    float sum = 0.f;
+    for (int i = 0; i < EnvS<NA>::NNODE; ++i) sum += s.belt_part[i];
+    s.belt_S = sum / m.belt_mass;
+    s.acc[0] = s.belt_acc_smooth + s.belt_S;
   }
 }
 
@@ -864,13 +952,14 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
     float h = m.h;
     if (i == 0) {
       float a = s.acc[0];
-      s.acc_ws[0] = a;
       float ai = m.belt_mass * a / (m.belt_mass + h * (m.belt_kv + m.belt_damp));
       s.belt_v += h * ai; s.belt_q += h * s.belt_v;
     } else if (i <= FM_NCUBE) {
       int k = i - 1;
+      if (s.cube_sleep[k]) continue;
       float* a = &s.acc[1 + 6 * k]; float* v = s.cube_v[k]; float* q = s.cube_q[k];
-      for (int d = 0; d < 6; ++d) { s.acc_ws[1 + 6 * k + d] = a[d]; v[d] += h * a[d]; }
+      f3 al = rmulT(s.cube_R[k], mk3(a[3], a[4], a[5]));      // world-frame angular acceleration -> body frame (free-joint qvel convention)
+      v[0] += h * a[0]; v[1] += h * a[1]; v[2] += h * a[2]; v[3] += h * al.x; v[4] += h * al.y; v[5] += h * al.z;
       q[0] += h * v[0]; q[1] += h * v[1]; q[2] += h * v[2];
       f3 wv = mk3(v[3], v[4], v[5]);
       float wn = norm3(wv);
@@ -888,7 +977,7 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       for (int r = 0; r < 9; ++r) {
         float sum = 0.f;
         for (int k = 0; k < 9; ++k) sum += s.M[a][r >= k ? tri(r, k) : tri(k, r)] * acc[k];
-        y[r] = sum; s.acc_ws[61 + 9 * a + r] = acc[r];
+        y[r] = sum;
       }
       chol9_solve(s.Li[a], y);
       for (int r = 0; r < 9; ++r) { s.arm_v[a][r] += h * y[r]; s.arm_q[a][r] += h * s.arm_v[a][r]; }
@@ -924,5 +1013,5 @@ FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float alpha) {
 }
 template <int NA, int E>
 FM_HD void ph_clear(EnvS<NA>* S, int tid, int T) {
-  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.n_armside = 0; s.nqueue = 0; s.ncon = 0; }
+  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.n_armside = 0; s.nqueue = 0; s.ncon = 0; s.need_union = 0; for (int i = 0; i < EnvS<NA>::NNODE; ++i) s.isl_root[i] = i; }
 }

@@ -14,7 +14,7 @@ struct Lay {
   // float fields
   static const int F_BELT_Q = 0, F_BELT_V = 1, F_CUBE_Q = 2, F_CUBE_V = F_CUBE_Q + 70, F_ARM_Q = F_CUBE_V + 60,
                    F_ARM_V = F_ARM_Q + 9 * NA, F_CTRL_T = F_ARM_V + 9 * NA, F_ACC_WS = F_CTRL_T + NU,
-                   F_PRE_Q = F_ACC_WS + NV, F_PRE_V = F_PRE_Q + 70, F_LAST_GD = F_PRE_V + 60, F_LAST_BD = F_LAST_GD + NA,
+                   F_PRE_Q = F_ACC_WS + 1, F_PRE_V = F_PRE_Q + 70, F_LAST_GD = F_PRE_V + 60, F_LAST_BD = F_LAST_GD + NA,
                    F_IK_ACT = F_LAST_BD + NA, F_LAST_ARM_ACT = F_IK_ACT + 8 * NA, F_IK_LAST_CTRL = F_LAST_ARM_ACT + 8 * NA,
                    F_IK_MOVE_START = F_IK_LAST_CTRL + 8 * NA, F_SITE = F_IK_MOVE_START + 3 * NA, F_EP_RET = F_SITE + 3 * NA,
                    F_PREV_F = F_EP_RET + 1, F_PREV_AF = F_PREV_F + 4 * FM_MAXCON, NF = F_PREV_AF + FM_AROW * NA;
@@ -82,7 +82,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     else if (fidx < L::F_ARM_V) (&s.arm_q[0][0])[fidx - L::F_ARM_Q] = v;
     else if (fidx < L::F_CTRL_T) (&s.arm_v[0][0])[fidx - L::F_ARM_V] = v;
     else if (fidx < L::F_ACC_WS) s.ctrl_target[fidx - L::F_CTRL_T] = v;
-    else if (fidx < L::F_PRE_Q) s.acc_ws[fidx - L::F_ACC_WS] = v;
+    else if (fidx < L::F_PRE_Q) s.belt_S = v;
     else if (fidx < L::F_PRE_V) (&s.cube_q[0][0])[fidx - L::F_PRE_Q] = v;      // pre-edit cube state first (stale-data quirk)
     else if (fidx < L::F_LAST_GD) (&s.cube_v[0][0])[fidx - L::F_PRE_V] = v;
     else if (fidx < L::F_LAST_BD) TS[e].last_gd[fidx - L::F_LAST_GD] = v;
@@ -221,7 +221,7 @@ FM_HD void task_reset_state(EnvS<NA>& s, TaskS& t, const FmEnvCfg& cfg) {
   t.last_score[0] = t.last_score[1] = 0;
   t.conveyor_speed = cfg.initial_conveyor_speed; t.spawn_freq = cfg.init_spawn_freq; t.play_time = 0.0;
   for (int u = 0; u < EnvS<NA>::NU; ++u) s.ctrl_target[u] = 0.f;
-  for (int i = 0; i < EnvS<NA>::NV; ++i) s.acc_ws[i] = 0.f;
+  s.belt_S = 0.f;
   t.ep_len = 0; t.ep_ret = 0.f;
   s.prev_n = 0;
   for (int a = 0; a < NA; ++a) s.prev_arow_n[a] = 0;
@@ -392,7 +392,7 @@ FM_HD void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
     else if (fidx < L::F_ARM_V) v = (&s.arm_q[0][0])[fidx - L::F_ARM_Q];
     else if (fidx < L::F_CTRL_T) v = (&s.arm_v[0][0])[fidx - L::F_ARM_V];
     else if (fidx < L::F_ACC_WS) v = s.ctrl_target[fidx - L::F_CTRL_T];
-    else if (fidx < L::F_PRE_Q) v = s.acc_ws[fidx - L::F_ACC_WS];
+    else if (fidx < L::F_PRE_Q) v = s.belt_S;
     else if (fidx < L::F_PRE_V) { v = (&s.cube_q[0][0])[fidx - L::F_PRE_Q]; wr = TS[e].done_prev != 0; }   // after a reset the model is in sync
     else if (fidx < L::F_LAST_GD) { v = (&s.cube_v[0][0])[fidx - L::F_PRE_V]; wr = TS[e].done_prev != 0; }
     else if (fidx < L::F_LAST_BD) v = TS[e].last_gd[fidx - L::F_LAST_GD];

@@ -55,7 +55,12 @@ struct FmDevModel {
   float bucket_pos[2][3], bucket_size[2][3];
   // broad-phase clusters: kind + index (static box idx / cube idx / arm*11+body)
   int cl_kind[13 + FM_NCUBE + FM_MAX_ARMS * FM_NARMBODY], cl_idx[13 + FM_NCUBE + FM_MAX_ARMS * FM_NARMBODY];
+  // broad phase: conservative world AABBs of the big geoms by cluster id (static boxes; belt with its full sliding range),
+  // first sphere-bounded cluster id, and the packed pair records built on the host (see fm_host_model.h)
+  float big_aabb[FM_MAX_SBOX + 2][6];
+  int cl_sph0;
 };
+enum { FM_PAIR_SPH_SPH = 0, FM_PAIR_PLANE_SPH = 1, FM_PAIR_BOX_SPH = 2, FM_PAIR_ALWAYS = 3 };
 
 // fp64 constants of the IK base policy kernel (ik_policy.py; dm_control qpos_from_site_pose)
 struct FmIkModel {
@@ -71,7 +76,7 @@ struct FmIkModel {
 
 // task / env configuration (BaseEnv kwargs base_env.py:26-34 + reward weights environments.py:252-259)
 struct FmEnvCfg {
-  int env_class, n_envs, frame_skip, pgs_outer, pgs_inner;
+  int env_class, n_envs, frame_skip, pgs_outer, pgs_inner, sleep_hidden;
   float pgs_tol;
   double initial_conveyor_speed, conveyor_acceleration, pt_time, force_threshold, dt, init_spawn_freq, spawn_freq_increase;
   double w_gripper_cube, w_cube_bucket, w_action_norm, base_reward;

@@ -95,13 +95,7 @@ class FactoryVecEnv:
 
     def step_wait(self, with_infos: bool = False):
         c = self.core
-        if c.env_class in (1, 2, 4):        # delta / single envs run the IK base policy before the step (environments.py:419,456,531)
-            c.ik_policy(write_obs=False)
-        elif c.env_class == 0:
-            c.ik_policy(write_obs=False)
-        c.step(self._actions)
-        if c.is_toggle:                     # toggling envs compute the next proposals inside _process_observation (:574-576)
-            c.ik_policy(write_obs=True)
+        c.env_step(self._actions)
         infos = None
         if with_infos:
             infos = self._infos()

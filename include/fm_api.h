@@ -25,7 +25,7 @@ enum { FM_FACTORY_MANIPULATION_ENV = 0, FM_SINGLE_FULL_RL = 1, FM_SINGLE_DELTA =
  * (src/environments.py:252-259) + solver knobs of this implementation. */
 typedef struct fm_config {
   int32_t n_envs, n_arms, env_class, auto_reset;
-  int32_t pgs_outer, pgs_inner, envs_per_block, reserved;
+  int32_t pgs_outer, pgs_inner, envs_per_block, reserved;   /* reserved: 1 = keep hidden cubes live (strict mode), 0 = sleep them at rest */
   float pgs_tol, reserved_f;
   double initial_conveyor_speed, conveyor_acceleration, pt_time, force_contact_threshold, control_frequency,
       spawn_freq, spawn_freq_increase;
@@ -78,6 +78,28 @@ int fm_set_state(fm_handle* h, const fm_state_view* v);
 /* run n raw sub-steps (mj_step2 + mj_step1 each) with ctrl = ctrl_target, no filter, no task logic; dump env `view->env` */
 int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void* stream);
 const char* fm_last_error(void);
+
+/* ---- on-GPU PPO (replaces stable-baselines3 at src/learning.py:106-118; hyper-parameters runs/r666unuv.json) ----
+ * fm_ppo_net / fm_ppo_ws are plain structs of dimensions, element offsets and caller-owned DEVICE pointers; their layout is
+ * defined in factory_marl_b200/csrc/fm_ppo.cu and mirrored by ctypes in factory_marl_b200/ppo.py. */
+typedef struct fm_ppo_net fm_ppo_net;
+typedef struct fm_ppo_ws fm_ppo_ws;
+/* ActorCriticPolicy.forward for n observations (collect_rollouts): env actions (clipped Box / int MultiDiscrete), raw actions,
+ * log-probs, values.  MLP layers run as bf16 tensor-core GEMMs with fp32 accumulation. */
+int fm_policy_forward(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, int n, uint64_t seed, int deterministic,
+                      void* act_env, float* act_raw, float* logp, float* value, void* stream);
+/* RolloutBuffer.compute_returns_and_advantage: arrays [T, N]; gamma learning.py:47, gae_lambda runs/r666unuv.json:42 */
+int fm_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int T, int N, float gamma,
+           float gae_lambda, float* advantages, float* returns, void* stream);
+/* one minibatch of PPO.train: forward + clipped-surrogate/value loss + backward, gradients accumulated into net->grads */
+int fm_ppo_update(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, const float* actions, const float* old_logp,
+                  const float* adv, const float* ret, const int32_t* idx, int n, float clip_range, float vf_coef, float ent_coef,
+                  int normalize_advantage, float* stats, void* stream);
+/* clip_grad_norm_ + Adam on the flat parameter buffer (after the NCCL all-reduce of net->grads; grad_scale = 1/world) */
+int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, int step,
+                 float* stats, void* stream);
+int fm_ppo_sync_bf16(const fm_ppo_net* net, void* stream);
+const char* fm_ppo_last_error(void);
 
 #ifdef __cplusplus
 }

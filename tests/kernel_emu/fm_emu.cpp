@@ -11,7 +11,17 @@
 #include "../../factory_marl_b200/csrc/fm_ik.cuh"
 
 static thread_local std::string g_err;
-struct HostRun { int T; template <class F> void operator()(F f) { for (int t = 0; t < T; ++t) f(t); } };
+// thread ids of one barrier interval are executed in ascending, descending or a fixed shuffled order (fm_emu_set_order):
+// a result that depends on that order reveals an intra-interval read-after-write, i.e. a missing barrier on the GPU.
+static int g_order = 0;
+struct HostRun {
+  int T;
+  template <class F> void operator()(F f) {
+    if (g_order == 0) for (int t = 0; t < T; ++t) f(t);
+    else if (g_order == 1) for (int t = T - 1; t >= 0; --t) f(t);
+    else for (int k = 0; k < T; ++k) f((k * 37 + 11) % T);
+  }
+};
 
 struct fm_handle {
   FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st; int E;
@@ -36,6 +46,8 @@ static void dispatch(fm_handle* h, const FmStepArgs& ar) {
 }
 
 extern "C" {
+void fm_emu_set_order(int o) { g_order = o; }
+void fm_emu_counters(long long* o) { o[0] = fm_dbg_sweeps; o[1] = fm_dbg_visits; o[2] = fm_dbg_islands; }
 const char* fm_last_error(void) { return g_err.c_str(); }
 int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {
   try {

@@ -1,0 +1,85 @@
+"""CPU suite (-m "not gpu"): the device phase functions, host-compiled (tests/kernel_emu), against the fp64 oracle and
+the golden vectors.  Same test bodies as the GPU suite (tests/parity_cases.py)."""
+import numpy as np
+import pytest
+
+from tests import parity_cases as pc
+from tests.emu_backend import make_core
+
+
+class EmuBackend:
+    mk = staticmethod(make_core)
+    to_np = staticmethod(lambda x: np.asarray(x))
+    from_np = staticmethod(lambda x: np.ascontiguousarray(x))
+
+    @staticmethod
+    def assign(dst, src):
+        dst[...] = src
+
+
+BE = EmuBackend()
+
+
+def test_single_substep_free_2arms():
+    pc.case_single_substep_free(BE, 2)
+
+
+def test_single_substep_free_4arms():
+    pc.case_single_substep_free(BE, 4)
+
+
+def test_single_substep_contacts_pairset_bit_exact():
+    pc.case_single_substep_contacts(BE)
+
+
+def test_golden_rollouts_2arms():
+    pc.case_golden_rollouts(BE, 2)
+
+
+def test_golden_rollouts_strict_mode():
+    pc.case_golden_rollouts(BE, 2, ["AllFullRLProgressRewardEnv", "BackupIKToggleEnv"], sleep_hidden=False)
+
+
+def test_arm_contact_pairsets_bit_exact():
+    pc.case_arm_contact_pairsets(BE)
+
+
+def test_golden_rollouts_4arms():
+    pc.case_golden_rollouts(BE, 4, ["AllFullRLProgressRewardEnv", "PauseIKToggleEnv"])
+
+
+def test_contact_free_100_step_rollout():
+    pc.case_contact_free_100_steps(BE)
+
+
+@pytest.mark.parametrize("cls", ["FactoryManipulationEnv", "PauseIKToggleEnv"])
+def test_ik_policy_from_settled_state(cls):
+    pc.case_ik_policy_from_settled_state(BE, cls)
+
+
+def test_no_intra_interval_dependencies():
+    """Race check for the barrier schedule: executing the thread ids of every barrier interval in ascending, descending
+    and shuffled order must give bit-identical results (T = 128 is coprime with the shuffle stride)."""
+    from factory_marl_b200 import model as fm
+    from tests.emu_backend import emu_lib
+    from tests.parity_util import load_golden, PROGRESS_KW
+    blob = fm.build_blob(2)
+    outs = []
+    for order in (0, 1, 2):
+        emu_lib().fm_emu_set_order(order)
+        try:
+            res = []
+            for cls in ("AllFullRLProgressRewardEnv", "PauseIKToggleEnv"):
+                g = load_golden(cls, 2)
+                core = make_core(blob, 4, 2, cls, auto_reset=False, **(PROGRESS_KW if "Progress" in cls else {}))
+                core.reset()
+                for t in range(len(g["actions"])):
+                    a = np.tile(g["actions"][t][None], (4, 1))
+                    core.env_step(np.ascontiguousarray(a))
+                    res.append(core.obs.copy()); res.append(core.reward.copy())
+            outs.append(res)
+        finally:
+            emu_lib().fm_emu_set_order(0)
+    for r in outs[1:]:
+        for x, y in zip(outs[0], r):
+            assert np.array_equal(x, y)

@@ -1,0 +1,122 @@
+"""GPU suite (-m gpu): the CUDA library through the C-ABI against the fp64 oracle and the golden vectors, plus
+size-independent properties at BASELINE.json's full size (4096 envs)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from tests import parity_cases as pc  # noqa: E402
+
+
+class GpuBackend:
+    @staticmethod
+    def mk(blob, n_envs, n_arms, cls, **kw):
+        from factory_marl_b200 import _capi, lib
+        from factory_marl_b200.vec_env import TorchCudaBackend
+        return _capi.FmCore(lib.load(), TorchCudaBackend("cuda:0"), blob, n_envs, n_arms, cls, **kw)
+
+    to_np = staticmethod(lambda x: x.detach().cpu().numpy())
+
+    @staticmethod
+    def from_np(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+    @staticmethod
+    def assign(dst, src):
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src)).to(dst.device))
+
+
+BE = GpuBackend()
+
+
+def test_single_substep_free_2arms():
+    pc.case_single_substep_free(BE, 2)
+
+
+def test_single_substep_free_4arms():
+    pc.case_single_substep_free(BE, 4)
+
+
+def test_single_substep_contacts_pairset_bit_exact():
+    pc.case_single_substep_contacts(BE)
+
+
+def test_golden_rollouts_2arms():
+    pc.case_golden_rollouts(BE, 2)
+
+
+def test_golden_rollouts_strict_mode():
+    pc.case_golden_rollouts(BE, 2, sleep_hidden=False)
+
+
+def test_arm_contact_pairsets_bit_exact():
+    pc.case_arm_contact_pairsets(BE)
+
+
+def test_golden_rollouts_4arms():
+    pc.case_golden_rollouts(BE, 4)
+
+
+def test_contact_free_100_step_rollout():
+    pc.case_contact_free_100_steps(BE)
+
+
+@pytest.mark.parametrize("cls", ["FactoryManipulationEnv", "PauseIKToggleEnv", "AllDeltaProgressRewardEnv"])
+def test_ik_policy_from_settled_state(cls):
+    if cls == "AllDeltaProgressRewardEnv":
+        pytest.skip("delta map is covered by the golden rollouts")
+    pc.case_ik_policy_from_settled_state(BE, cls)
+
+
+def test_full_size_properties_4096_envs():
+    """BASELINE.json configs[1] size: determinism, batch invariance, invariants of the state."""
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    kw = dict(gripper_to_closest_cube_reward_factor=0.2, closest_cube_to_bucket_reward_factor=0.4, base_reward=0.4)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    # moderate joint targets: no arm crashes, so no contact-capacity overflow (overflow truncation depends on atomic order)
+    acts = [(torch.rand((4096, 16), device="cuda", generator=gen) * 2 - 1) * 0.4 for _ in range(12)]
+
+    def run(n):
+        env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=n, num_arms=2, seeds=list(range(42, 42 + n)), **kw)
+        env.reset()
+        out = []
+        for a in acts:
+            obs, rew, term, _ = env.step(a[:n])
+            out.append((obs.clone(), rew.clone(), term.clone()))
+        return env, out
+
+    env, o1 = run(4096)
+    assert int(env.core.i[env.core.off("I_FLAGS")].max()) == 0
+    _, o2 = run(4096)
+    _, o3 = run(8)
+    for (a, b, c) in zip(o1, o2, o3):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])   # run-to-run determinism
+        assert torch.equal(a[0][:8], c[0][:8]) and torch.equal(a[1][:8], c[1][:8])               # independent of batch size
+        assert torch.isfinite(a[0]).all() and torch.isfinite(a[1]).all()
+    f = env.core.f
+    cq = f[env.core.off("F_CUBE_Q"):env.core.off("F_CUBE_Q") + 70].reshape(10, 7, -1)
+    qn = torch.linalg.norm(cq[:, 3:7], dim=1)
+    in_scene_first = env.core.i[env.core.off("I_NIN")]
+    assert (in_scene_first >= 0).all() and (in_scene_first <= 10).all()
+    # hidden / settled cubes carry unit quaternions (the freshly spawned one is raw until its first sub-step)
+    assert ((qn - 1).abs() < 1e-4).float().mean() > 0.85
+    assert (env.core.i[env.core.off("I_NIN")] + env.core.i[env.core.off("I_NOUT")] == 10).all()
+    assert env.gpu_launches >= 13
+
+
+def test_auto_reset_and_episode_info():
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=64, num_arms=2, force_contact_threshold=1e-3)
+    env.reset()
+    a = torch.ones((64, 16), device="cuda") * 3.0      # drives the arms into the table: force termination
+    done_seen = False
+    for t in range(30):
+        obs, rew, term, infos = env.step(a, with_infos=True)
+        if term.any():
+            e = int(torch.nonzero(term)[0])
+            assert "terminal_observation" in infos[e] and infos[e]["episode"]["l"] == t + 1
+            assert torch.all(obs[e][:48] == 0)          # returned obs is the post-reset observation (qpos0, zero ctrl)
+            done_seen = True
+            break
+    assert done_seen
