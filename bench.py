@@ -206,6 +206,25 @@ def run_ours(args):
     h2d = host_act.numel() * 4
     d2h = host_obs.numel() * 4 + host_rew.numel() * 4 + host_done.numel()
 
+    # ---- secondary metric (BASELINE.json: "PPO train samples/sec"): one PPO iteration = rollout of n_steps + 10 epochs of updates,
+    # SB3 hyper-parameters under the declared large-batch mapping; gradients all-reduced over NCCL when world > 1
+    ppo_info = None
+    if not args.no_ppo:
+        algo = fppo.PPO(env, n_steps=args.ppo_steps, batch_size=min(8192, args.ppo_steps * n), n_epochs=10, seed=0)
+        algo.collect_rollouts(); algo.train()                       # warm-up iteration
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        p0, p1, p2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        p0.record(); algo.collect_rollouts(); p1.record(); info = algo.train(); p2.record(); torch.cuda.synchronize()
+        tp = torch.tensor([p0.elapsed_time(p2), p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        samples = world * n * args.ppo_steps
+        ppo_info = {"samples_per_s": samples / (float(tp[0]) * 1e-3), "rollout_ms": float(tp[1]), "update_ms": float(tp[0] - tp[1]),
+                    "samples": samples, "n_steps": args.ppo_steps, "batch_size": algo.batch_size, "n_epochs": 10,
+                    "optimizer_steps": info["n_updates"], "approx_kl": info["approx_kl"], "clip_fraction": info["clip_fraction"],
+                    "grad_allreduce": "nccl" if world > 1 else "none"}
     if rank == 0:
         hbm_peak, peak_kind, sm_max = peaks()
         nf, nd, ni = env.core.f.shape[0], env.core.d.shape[0], env.core.i.shape[0]
@@ -224,6 +243,8 @@ def run_ours(args):
                                   "peak_source": "148 SM x 128 lanes x 2 x max SM clock"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": sampler.result()}
+        if ppo_info is not None:
+            line["ppo_train"] = ppo_info
         if world == 1 and not args.no_cpu:
             rate, cores, sample, wall = cpu_reference_rate(args.cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
@@ -241,6 +262,8 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-steps", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -179,3 +179,38 @@ FM_HD int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 B
   }
   return cnt;
 }
+
+// Fast path of col_box_box for a small box resting on / falling onto the top face of a big AXIS-ALIGNED box (belt, table,
+// bucket floor): when the small box's bounding sphere lies horizontally inside the top face and its centre is above it,
+// the separating-axis search of col_box_box always selects the big box's +z face (see tests: fm_emu_check_box_on_face),
+// no clipping happens, and the contacts are the vertices of the incident face below the surface, in the same order.
+// `big_is_1`: the big box is geom1 (normal +z) or geom2 (normal -z).  Returns -1 when the fast path does not apply.
+FM_HD int col_box_on_face(f3 pb, f3 hb, f3 pc, const float* Rc, f3 hc, bool big_is_1, RawC* out) {
+  float r = norm3(hc);
+  float top = pb.z + hb.z;
+  if (!(fminf(hb.x, hb.y) >= 0.25f) || pc.z < top || fabsf(pc.x - pb.x) + r > hb.x || fabsf(pc.y - pb.y) + r > hb.y) return -1;
+  if (pc.z - r > top) return 0;
+  f3 nr = mk3(0, 0, 1);
+  int iax = 0; float mn = 1e30f, isg = 1.f;
+  for (int k = 0; k < 3; ++k) {
+    float dd = dot3(rcol(Rc, k), nr);
+    if (dd < mn) { mn = dd; iax = k; isg = 1.f; }
+    if (-dd < mn) { mn = -dd; iax = k; isg = -1.f; }
+  }
+  int i1 = (iax + 1) % 3, i2 = (iax + 2) % 3;
+  f3 fc = pc + rcol(Rc, iax) * (isg * comp3(hc, iax));
+  f3 e1 = rcol(Rc, i1) * comp3(hc, i1), e2 = rcol(Rc, i2) * comp3(hc, i2);
+  f3 rc = mk3(pb.x, pb.y, top);
+  f3 n = big_is_1 ? nr : nr * -1.0f;
+  int cnt = 0;
+  for (int k = 0; k < 4; ++k) {
+    f3 q = fc + e1 * ((k == 0 || k == 3) ? 1.f : -1.f) + e2 * ((k < 2) ? 1.f : -1.f);
+    f3 dq = q - rc;
+    float hgt = dq.z;
+    if (hgt > 0.f) continue;
+    out[cnt].pos = rc + mk3(1, 0, 0) * dq.x + mk3(0, 1, 0) * dq.y + nr * (hgt * 0.5f);
+    out[cnt].n = n; out[cnt].dist = hgt;
+    cnt++;
+  }
+  return cnt;
+}

@@ -52,6 +52,7 @@ inline void fm_build_host_model(const void* blob, size_t n, FmHostModel& H) {
     for (int k = 0; k < 3; ++k) { m.sbox_pos[i][k] = (float)sb[15 * i + k]; m.sbox_half[i][k] = (float)sb[15 * i + 12 + k]; }
     for (int k = 0; k < 9; ++k) m.sbox_R[i][k] = (float)sb[15 * i + 3 + k];
     m.sbox_geom[i] = sbg[i]; m.sbox_class[i] = gclass[sbg[i]];
+    { const float* R = m.sbox_R[i]; m.sbox_aligned[i] = (R[0] == 1.f && R[4] == 1.f && R[8] == 1.f && R[1] == 0.f && R[2] == 0.f && R[3] == 0.f && R[5] == 0.f && R[6] == 0.f && R[7] == 0.f) ? 1 : 0; }
   }
   const double* bl = D(blob, n, "g_belt");
   for (int k = 0; k < 3; ++k) { m.belt_pos[k] = (float)bl[k]; m.belt_half[k] = (float)bl[3 + k]; }
@@ -83,6 +84,15 @@ inline void fm_build_host_model(const void* blob, size_t n, FmHostModel& H) {
   }
   const double* base = D(blob, n, "g_arm_base");
   for (int a = 0; a < m.n_arms; ++a) { for (int k = 0; k < 3; ++k) m.arm_base_pos[a][k] = (float)base[7 * a + k]; for (int k = 0; k < 4; ++k) m.arm_base_quat[a][k] = (float)base[7 * a + 3 + k]; }
+  auto quat_to_mat = [](const double* q, float* R) {
+    double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double w = q[0] / nq, x = q[1] / nq, y = q[2] / nq, z = q[3] / nq;
+    double Rd[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), w * w - x * x + y * y - z * z,
+                    2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+    for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+  };
+  for (int b = 0; b < FM_NARMBODY; ++b) quat_to_mat(ab + 25 * b + 3, m.ab_C[b]);
+  for (int a = 0; a < m.n_arms; ++a) quat_to_mat(base + 7 * a + 3, m.arm_base_R[a]);
   const double* sp = D(blob, n, "g_arm_sph", &c);
   if (c / 6 != FM_NSPH) throw std::runtime_error("unexpected arm sphere count");
   int prevb = -1;

@@ -9,6 +9,9 @@
 #include "fm_host_common.h"
 #include "fm_ik.cuh"
 
+#ifndef FM_DEFAULT_E
+#define FM_DEFAULT_E 4
+#endif
 static thread_local std::string g_err;
 #define FM_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return 2; } } while (0)
 
@@ -29,6 +32,7 @@ __global__ void __launch_bounds__(32 * E) fm_step_kernel(const FmDevModel* __res
     for (int i = threadIdx.x; i < nw; i += 32 * E) z[i] = 0;
     __syncthreads();
   }
+  __builtin_assume(__isShared(S)); __builtin_assume(__isShared(TS));
   DevRun run;
   fm_block_step<NA, E>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
 }
@@ -62,9 +66,12 @@ static int launch_step(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
 static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
   if (h->hm.n_arms == 2) {
-    if (h->E == 8) return launch_step<2, 8>(h, ar, s);
+    if (h->E == 1) return launch_step<2, 1>(h, ar, s);
+    if (h->E == 2) return launch_step<2, 2>(h, ar, s);
     return launch_step<2, 4>(h, ar, s);
   }
+  if (h->E == 1) return launch_step<4, 1>(h, ar, s);
+  if (h->E == 2) return launch_step<4, 2>(h, ar, s);
   return launch_step<4, 4>(h, ar, s);
 }
 
@@ -82,7 +89,7 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (cfg->env_class < 0 || cfg->env_class > 6) throw std::runtime_error("bad env_class");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
     int E = cfg->envs_per_block;
-    h->E = (h->hm.n_arms == 2 && E == 8) ? 8 : 4;
+    h->E = (E == 1 || E == 2 || E == 4) ? E : FM_DEFAULT_E;
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs};
     FM_CUDA(cudaMalloc(&h->d_model, sizeof(FmDevModel)));
     FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));

@@ -39,6 +39,13 @@ static long long fm_dbg_sweeps = 0, fm_dbg_visits = 0, fm_dbg_islands = 0;   // 
 #else
 #define FM_DBG(x)
 #endif
+#if defined(__CUDA_ARCH__)
+#define FM_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define FM_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define FM_ASSUME_SHARED(p)
+#define FM_ASSUME_GLOBAL(p)
+#endif
 #define FM_QMAX 96
 #define FM_AROW 10   // equality + up to 9 limit rows per arm
 
@@ -58,7 +65,7 @@ struct EnvS {
   int cube_sleep[FM_NCUBE];
   float cube_R[FM_NCUBE][9], cube_x[FM_NCUBE][3], cube_vw[FM_NCUBE][6];   // cube_vw: (v, R*omega_local)
   float body_x[NA][FM_NARMBODY][3], body_R[NA][FM_NARMBODY][9];
-  float bnd[FM_NCUBE + NA * FM_NARMBODY][4];   // bounding spheres (x, y, z, r) of the cube / arm-body clusters
+  alignas(16) float bnd[FM_NCUBE + NA * FM_NARMBODY][4];   // bounding spheres (x, y, z, r) of the cube / arm-body clusters
   float M[NA][45], Minv[NA][81], Li[NA][45], Lc[NA][45];
   float bias[NA][9];
   // ---- acceleration stage
@@ -127,6 +134,7 @@ FM_HD int dof_body(int d) { return d < 7 ? d + 1 : d + 2; }
 // phase: cube kinematics (normalise quats in place as mj_kinematics does [3P])
 template <int NA, int E>
 FM_HD void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int sleep_hidden) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < FM_NCUBE * E; w += T) {
     EnvS<NA>& s = S[w % E]; int k = w / E;
     q4 q = qnormf(mkq(s.cube_q[k][3], s.cube_q[k][4], s.cube_q[k][5], s.cube_q[k][6]));
@@ -155,40 +163,36 @@ FM_HD void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int 
 // One thread per (env, arm); world-aligned axes, link-origin reference points.
 template <int NA, int E>
 FM_HD void ph_arm_fk(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool with_vel) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * E; w += T) {
     EnvS<NA>& s = S[w % E]; int a = w / E;
-    q4 q = mkq(m.arm_base_quat[a][0], m.arm_base_quat[a][1], m.arm_base_quat[a][2], m.arm_base_quat[a][3]);
+    // rotation matrices are propagated directly: R_b = R_parent * C_b * Rz(q_b) with the constant body rotation C_b
+    // (iiwa14.xml frame quats) precomputed by the host; a hinge only mixes the first two columns.
     f3 x = ld3(m.arm_base_pos[a]);
     float Rp[9];
-    q2matf(q, Rp);
+    for (int i = 0; i < 9; ++i) { Rp[i] = m.arm_base_R[a][i]; s.body_R[a][0][i] = Rp[i]; }
     st3(s.body_x[a][0], x);
-    for (int i = 0; i < 9; ++i) s.body_R[a][0][i] = Rp[i];
     f3 om = mk3(0, 0, 0), al = mk3(0, 0, 0), ap = mk3(0, 0, m.g);
     if (with_vel) { st3(s.d_om[a][0], om); st3(s.d_al[a][0], al); st3(s.d_ap[a][0], ap); }
-    // gripper base frame kept for the two plates
-    q4 q8 = q; f3 x8 = x, om8 = om, al8 = al, ap8 = ap; float R8[9];
+    f3 x8 = x, om8 = om, al8 = al, ap8 = ap; float R8[9];
     for (int b = 1; b < FM_NARMBODY; ++b) {
-      if (b >= 9) { q = q8; x = x8; om = om8; al = al8; ap = ap8; for (int i = 0; i < 9; ++i) Rp[i] = R8[i]; }
+      if (b >= 9) { x = x8; om = om8; al = al8; ap = ap8; for (int i = 0; i < 9; ++i) Rp[i] = R8[i]; }
       f3 r = rmul(Rp, ld3(m.ab_pos[b]));
-      q = qmulf(q, mkq(m.ab_quat[b][0], m.ab_quat[b][1], m.ab_quat[b][2], m.ab_quat[b][3]));
-      int d = ab_dof(b);
+      const float* Cb = m.ab_C[b];
       float R[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = Rp[3 * i] * Cb[j] + Rp[3 * i + 1] * Cb[3 + j] + Rp[3 * i + 2] * Cb[6 + j];
+      int d = ab_dof(b);
       f3 axv = mk3(0, 0, 0);
       if (m.ab_jtype[b] == 1) {
         float sn, cs;
-        sincosf(0.5f * s.arm_q[a][d], &sn, &cs);
-        q = qmulf(q, mkq(cs, 0, 0, sn));
-        if (b == 4) q = qnormf(q);
-        q2matf(q, R);
+        sincosf(s.arm_q[a][d], &sn, &cs);
+        for (int i = 0; i < 3; ++i) { float c0 = R[3 * i], c1 = R[3 * i + 1]; R[3 * i] = cs * c0 + sn * c1; R[3 * i + 1] = cs * c1 - sn * c0; }
         if (with_vel) axv = rcol(R, 2) * s.arm_v[a][d];
       } else if (m.ab_jtype[b] == 2) {
-        q2matf(q, R);
         f3 ax = rcol(R, 0);
         r = r + ax * s.arm_q[a][d];
         if (with_vel) axv = ax * s.arm_v[a][d];
-      } else {
-        q = qnormf(q);      // gripper base: renormalise once before the plates branch off
-        q2matf(q, R);
       }
       if (with_vel) {
         // acceleration of the new origin (bias part, qacc = 0), then angular quantities
@@ -200,7 +204,7 @@ FM_HD void ph_arm_fk(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool with
       x = x + r;
       st3(s.body_x[a][b], x);
       for (int i = 0; i < 9; ++i) { s.body_R[a][b][i] = R[i]; Rp[i] = R[i]; }
-      if (b == 8) { q8 = q; x8 = x; om8 = om; al8 = al; ap8 = ap; for (int i = 0; i < 9; ++i) R8[i] = R[i]; }
+      if (b == 8) { x8 = x; om8 = om; al8 = al; ap8 = ap; for (int i = 0; i < 9; ++i) R8[i] = R[i]; }
     }
   }
 }
@@ -208,6 +212,7 @@ FM_HD void ph_arm_fk(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool with
 // phase: per-body quantities (parallel): COM offset, world inertia, composite init, NE body wrench, cluster centre
 template <int NA, int E>
 FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
     const float* R = s.body_R[a][b];
@@ -250,6 +255,7 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // phase: backward recursions (thread per arm): composite inertias about body origins, NE wrench accumulation, bias
 template <int NA, int E>
 FM_HD void ph_arm_backward(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * E; w += T) {
     EnvS<NA>& s = S[w % E]; int a = w / E;
     for (int b = FM_NARMBODY - 1; b >= 2; --b) {
@@ -282,6 +288,7 @@ FM_HD void ph_arm_backward(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // phase: mass matrix entries M_ij (parallel over 45 pairs per arm) from composite inertias (CRBA)
 template <int NA, int E>
 FM_HD void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * 45 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ap = w / E; int a = ap / 45, pr = ap % 45;
     int i = 0; while ((i + 1) * (i + 2) / 2 <= pr) ++i;
@@ -308,6 +315,7 @@ FM_HD void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // phase: Cholesky factors (thread per arm): Lc = chol(M), Li = chol(M - h*D) with D = d(actuator force)/d(qvel) [3P implicitfast]
 template <int NA, int E>
 FM_HD void ph_arm_chol(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < 2 * NA * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ai = w / E; int a = ai >> 1, which = ai & 1;
     float L[45];
@@ -354,6 +362,7 @@ FM_HD void chol9_solve(const float* L, float* x) {
 // phase: explicit inverse, one column per thread
 template <int NA, int E>
 FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
   for (int w = tid; w < NA * 9 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ac = w / E; int a = ac / 9, c = ac % 9;
     float x[9];
@@ -377,30 +386,41 @@ FM_HD void cluster_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx
   }
 }
 
+struct alignas(16) bnd4 { float x, y, z, r; };
 template <int NA, int E>
 FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int np = m.n_cluster_pair, s0 = m.cl_sph0;
-  for (int w = tid; w < np * E; w += T) {
-    EnvS<NA>& s = S[w % E]; int pi = w / E;
-    unsigned rec = cpairs[pi];
-    int c1 = rec & 255, c2 = (rec >> 8) & 255, type = rec >> 16;
-    const float* b2 = s.bnd[c2 - s0];
-    bool far;
-    if (b2[3] < 0.f) far = true;                       // sleeping cube
-    else if (type == FM_PAIR_SPH_SPH) {
-      const float* b1 = s.bnd[c1 - s0];
-      if (b1[3] < 0.f) continue;
-      float dx = b1[0] - b2[0], dy = b1[1] - b2[1], dz = b1[2] - b2[2], rr = b1[3] + b2[3];
-      far = dx * dx + dy * dy + dz * dz > rr * rr;
-    } else if (type == FM_PAIR_BOX_SPH) {
-      const float* bx = m.big_aabb[c1];
-      float dx = fmaxf(fmaxf(bx[0] - b2[0], b2[0] - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - b2[1], b2[1] - bx[4]), 0.f), dz = fmaxf(fmaxf(bx[2] - b2[2], b2[2] - bx[5]), 0.f);
-      far = dx * dx + dy * dy + dz * dz > b2[3] * b2[3];
-    } else if (type == FM_PAIR_PLANE_SPH) far = b2[2] - b2[3] > 0.f;
-    else far = false;
-    if (far) continue;
-    int slot = FM_ATOMIC_ADD(&s.nqueue, 1);
-    if (slot < FM_QMAX) s.queue[slot] = (unsigned short)pi; else FM_ATOMIC_OR(&s.flags, FM_FLAG_QUEUE_OVERFLOW);
+  EnvS<NA>& s = S[tid % E];                              // T is a multiple of E: a thread always serves the same env
+  const bnd4* bnd = reinterpret_cast<const bnd4*>(&s.bnd[0][0]) - s0;
+  const int stride = T / E;
+  for (int p0 = tid / E; p0 < np; p0 += 4 * stride) {
+    // four pair records are fetched up front so their global-load latencies overlap
+    unsigned recs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { int pi = p0 + u * stride; recs[u] = pi < np ? cpairs[pi] : 0xFFFFFFFFu; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      unsigned rec = recs[u];
+      if (rec == 0xFFFFFFFFu) continue;
+      int c1 = rec & 255, c2 = (rec >> 8) & 255, type = rec >> 16;
+      bnd4 b2 = bnd[c2];
+      bool far;
+      if (b2.r < 0.f) far = true;                          // sleeping cube
+      else if (type == FM_PAIR_SPH_SPH) {
+        bnd4 b1 = bnd[c1];
+        float dx = b1.x - b2.x, dy = b1.y - b2.y, dz = b1.z - b2.z, rr = b1.r + b2.r;
+        far = b1.r < 0.f || dx * dx + dy * dy + dz * dz > rr * rr;
+      } else if (type == FM_PAIR_BOX_SPH) {
+        const float* bx = m.big_aabb[c1];
+        float dx = fmaxf(fmaxf(bx[0] - b2.x, b2.x - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - b2.y, b2.y - bx[4]), 0.f), dz = fmaxf(fmaxf(bx[2] - b2.z, b2.z - bx[5]), 0.f);
+        far = dx * dx + dy * dy + dz * dz > b2.r * b2.r;
+      } else if (type == FM_PAIR_PLANE_SPH) far = b2.z - b2.r > 0.f;
+      else far = false;
+      if (far) continue;
+      int slot = FM_ATOMIC_ADD(&s.nqueue, 1);
+      if (slot < FM_QMAX) s.queue[slot] = (unsigned short)(p0 + u * stride); else FM_ATOMIC_OR(&s.flags, FM_FLAG_QUEUE_OVERFLOW);
+    }
   }
 }
 
@@ -419,23 +439,28 @@ FM_HD void emit(EnvS<NA>& s, int g1, int g2, int side1, int side2, bool armgeom,
   }
 }
 
-struct GeomBox { f3 p; const float* R; f3 hs; int geom, side, cls; };
+struct GeomBox { f3 p; const float* R; f3 hs; int geom, side, cls, axis_aligned; };
 
 template <int NA>
 FM_HD void get_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, int sub, GeomBox& g, float* Rid) {
-  if (kind == FM_CL_SBOX) { g.p = ld3(m.sbox_pos[idx]); g.R = m.sbox_R[idx]; g.hs = ld3(m.sbox_half[idx]); g.geom = m.sbox_geom[idx]; g.side = pack_side(FM_SIDE_STATIC, 0, 0); g.cls = m.sbox_class[idx]; }
-  else if (kind == FM_CL_BELT) { cluster_box(s, m, kind, idx, g.p, g.R, g.hs, Rid); g.geom = m.belt_geom; g.side = pack_side(FM_SIDE_BELT, 0, 0); g.cls = m.belt_class; }
-  else if (kind == FM_CL_CUBE) { g.p = ld3(s.cube_x[idx]); g.R = s.cube_R[idx]; float h = m.cube_half[idx]; g.hs = mk3(h, h, h); g.geom = m.cube_geom[idx]; g.side = pack_side(FM_SIDE_CUBE, idx, 0); g.cls = m.cube_class; }
+  if (kind == FM_CL_SBOX) { g.p = ld3(m.sbox_pos[idx]); g.R = m.sbox_R[idx]; g.hs = ld3(m.sbox_half[idx]); g.geom = m.sbox_geom[idx]; g.side = pack_side(FM_SIDE_STATIC, 0, 0); g.cls = m.sbox_class[idx]; g.axis_aligned = m.sbox_aligned[idx]; }
+  else if (kind == FM_CL_BELT) { cluster_box(s, m, kind, idx, g.p, g.R, g.hs, Rid); g.geom = m.belt_geom; g.side = pack_side(FM_SIDE_BELT, 0, 0); g.cls = m.belt_class; g.axis_aligned = 1; }
+  else if (kind == FM_CL_CUBE) { g.p = ld3(s.cube_x[idx]); g.R = s.cube_R[idx]; float h = m.cube_half[idx]; g.hs = mk3(h, h, h); g.geom = m.cube_geom[idx]; g.side = pack_side(FM_SIDE_CUBE, idx, 0); g.cls = m.cube_class; g.axis_aligned = 0; }
   else {  // arm body box `sub`
     int a = idx / FM_NARMBODY, b = idx % FM_NARMBODY;
     g.R = s.body_R[a][b]; g.p = ld3(s.body_x[a][b]) + rmul(g.R, ld3(m.abox_pos[sub])); g.hs = ld3(m.abox_half[sub]);
-    g.geom = m.arm_first_geom[a] + m.abox_geom[sub]; g.side = pack_side(FM_SIDE_ARM, a * 16 + b, 0); g.cls = m.abox_class;
+    g.geom = m.arm_first_geom[a] + m.abox_geom[sub]; g.side = pack_side(FM_SIDE_ARM, a * 16 + b, 0); g.cls = m.abox_class; g.axis_aligned = 0;
   }
 }
 
 template <int NA>
 FM_HD void pair_box_box(EnvS<NA>& s, const GeomBox& x, const GeomBox& y, bool armgeom) {
   const GeomBox& g1 = x.geom < y.geom ? x : y; const GeomBox& g2 = x.geom < y.geom ? y : x;
+  if (g1.axis_aligned && !g2.axis_aligned) {      // small box on the top face of a big axis-aligned box (belt, table): fast path.
+    RawC rf[4];                                   // Only with the big box as geom1: on exact face-axis ties the general routine
+    int nf = col_box_on_face(g1.p, g1.hs, g2.p, g2.R, g2.hs, true, rf);   // prefers box 1's face, which must be the big one.
+    if (nf >= 0) { emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rf, nf); return; }
+  }
   if (far_sphere_box(g2.p, norm3(g2.hs), g1.p, g1.R, g1.hs) || far_sphere_box(g1.p, norm3(g1.hs), g2.p, g2.R, g2.hs)) return;
   RawC rc[8];
   int n = col_box_box(g1.p, g1.R, g1.hs, g2.p, g2.R, g2.hs, rc);
@@ -486,6 +511,7 @@ FM_HD void narrow_arm_geom_vs(EnvS<NA>& s, const FmDevModel& m, int a2, int b2, 
 
 template <int NA, int E>
 FM_HD void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   int mq = 0;
   for (int e = 0; e < E; ++e) mq = S[e].nqueue > mq ? S[e].nqueue : mq;
   if (mq > FM_QMAX) mq = FM_QMAX;
@@ -587,6 +613,7 @@ FM_HD void side_apply(const SideW& o, f3 n, f3 t1, f3 t2, float* cube, float* ar
 
 template <int NA, int E>
 FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < FM_MAXCON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ri = w / E;
     int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
@@ -700,6 +727,7 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
 // phase: arm-local rows (thread per arm): joint equality q_l - q_r = 0 and joint limits
 template <int NA, int E>
 FM_HD void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * E; w += T) {
     EnvS<NA>& s = S[w % E]; int a = w / E;
     int nr = 0;
@@ -743,6 +771,7 @@ FM_HD void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // contact lists are built fully in parallel (ph_island_lists).  Otherwise one thread per env runs a union-find first.
 template <int NA, int E>
 FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
@@ -764,6 +793,7 @@ FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
 }
 template <int NA, int E>
 FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < (FM_MAXCON + NN + 1) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
@@ -788,6 +818,7 @@ FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
 // phase: actuation + smooth acceleration (mj_fwdActuation, mj_fwdAcceleration)
 template <int NA, int E>
 FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int per = 1 + FM_NCUBE + 9 * NA;
   for (int w = tid; w < per * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
@@ -891,6 +922,7 @@ FM_HD float arm_rows_visit(EnvS<NA>& s, int a, bool first) {
 
 template <int NA, int E>
 FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < NN * E; w += T) {
     EnvS<NA>& s = S[w % E]; int node = w / E;
@@ -920,6 +952,7 @@ FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
 // belt dof is held at its smooth acceleration plus the previous sub-step's contact term (the coupling is ~1e-3 of a cube's).
 template <int NA, int E>
 FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
     float sum = 0.f;
@@ -932,6 +965,7 @@ FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // phase: force-termination statistic on the forces of this solve (base_env.py:226-236; clarification SURVEY.md A.2)
 template <int NA, int E>
 FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
   for (int w = tid; w < FM_MAXCON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
     if (c >= s.ncon || !((s.c_side[c] >> 30) & 1)) continue;
@@ -946,6 +980,7 @@ FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
 // phase: implicitfast velocity update + semi-implicit position integration (mj_implicit, mj_advance) [3P]
 template <int NA, int E>
 FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int per = 1 + FM_NCUBE + NA;
   for (int w = tid; w < per * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
@@ -988,6 +1023,7 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // phase: remember this solve's forces for the next warm start
 template <int NA, int E>
 FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
   for (int w = tid; w < (FM_MAXCON + NA) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
     if (c < FM_MAXCON) {
@@ -1004,6 +1040,7 @@ FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
 // phase: PT1 control filter (base_env.py:209-215) and per-substep counters reset
 template <int NA, int E>
 FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float alpha) {
+  FM_ASSUME_SHARED(S);
   const int NU = EnvS<NA>::NU;
   for (int w = tid; w < NU * E; w += T) {
     EnvS<NA>& s = S[w % E]; int u = w / E;
@@ -1013,5 +1050,6 @@ FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float alpha) {
 }
 template <int NA, int E>
 FM_HD void ph_clear(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
   for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.n_armside = 0; s.nqueue = 0; s.ncon = 0; s.need_union = 0; for (int i = 0; i < EnvS<NA>::NNODE; ++i) s.isl_root[i] = i; }
 }

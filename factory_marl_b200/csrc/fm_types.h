@@ -9,8 +9,8 @@
 #define FM_NSPH 46          // collision spheres per arm (iiwa14.xml:58-136)
 #define FM_NABOX 9          // gripper boxes per arm (gripper.xml:6-41)
 #define FM_MAX_SBOX 12      // table + 2 x (bucket floor + 4 fences)
-#define FM_MAXCON 64        // contacts per env
-#define FM_MAXARMSIDE 12    // contact sides that touch an arm (each stores 3x9 Jacobian + 3x9 Minv J^T)
+#define FM_MAXCON 56        // contacts per env
+#define FM_MAXARMSIDE 10    // contact sides that touch an arm (each stores 3x9 Jacobian + 3x9 Minv J^T)
 #define FM_MAX_ARMS 4
 #define FM_NCLASS 4
 
@@ -24,7 +24,7 @@ struct FmDevModel {
   float h, g;                      // timestep (scene.xml:2), |gravity|
   // static boxes (world frame): pos, rot (row-major), half size, contact class, geom id
   float sbox_pos[FM_MAX_SBOX][3], sbox_R[FM_MAX_SBOX][9], sbox_half[FM_MAX_SBOX][3];
-  int sbox_geom[FM_MAX_SBOX], sbox_class[FM_MAX_SBOX];
+  int sbox_geom[FM_MAX_SBOX], sbox_class[FM_MAX_SBOX], sbox_aligned[FM_MAX_SBOX];
   // belt (conveyor_belt.xml:4-11)
   float belt_pos[3], belt_half[3], belt_mass, belt_damp, belt_kv, belt_invw;
   int belt_geom, belt_class;
@@ -35,7 +35,8 @@ struct FmDevModel {
   // pair contact parameters by class: mu, solref0, solref1, solimp[5]
   float pair_param[FM_NCLASS][FM_NCLASS][8];
   // arm template
-  float arm_base_pos[FM_MAX_ARMS][3], arm_base_quat[FM_MAX_ARMS][4];
+  float arm_base_pos[FM_MAX_ARMS][3], arm_base_quat[FM_MAX_ARMS][4], arm_base_R[FM_MAX_ARMS][9];
+  float ab_C[FM_NARMBODY][9];      // constant rotation of each template body relative to its parent (from ab_quat)
   float ab_pos[FM_NARMBODY][3], ab_quat[FM_NARMBODY][4], ab_mass[FM_NARMBODY], ab_ipos[FM_NARMBODY][3], ab_I[FM_NARMBODY][6];
   int ab_jtype[FM_NARMBODY];       // 0 none, 1 hinge (local z), 2 slide (local x)
   float ab_range[FM_NARMBODY][2], ab_invw[FM_NARMBODY], ab_dofinvw[FM_NARMBODY];

@@ -5,6 +5,7 @@
 // The product (factory_marl_b200/) never loads this library; its ops fail loudly without the CUDA build.
 #include <cstdio>
 #include <cstdlib>
+#include <cstdio>
 #include <new>
 #include <vector>
 #include "../../factory_marl_b200/csrc/fm_host_common.h"
@@ -41,10 +42,41 @@ static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
   }
 }
 static void dispatch(fm_handle* h, const FmStepArgs& ar) {
-  if (h->hm.n_arms == 2) { if (h->E == 8) run_blocks<2, 8>(h, ar); else run_blocks<2, 4>(h, ar); }
-  else run_blocks<4, 4>(h, ar);
+  if (h->hm.n_arms == 2) { if (h->E == 1) run_blocks<2, 1>(h, ar); else if (h->E == 2) run_blocks<2, 2>(h, ar); else run_blocks<2, 4>(h, ar); }
+  else { if (h->E == 1) run_blocks<4, 1>(h, ar); else run_blocks<4, 4>(h, ar); }
 }
 
+// randomised equivalence check of the box-on-face fast path against the general separating-axis routine
+static unsigned long long lcg(unsigned long long& x) { x = x * 6364136223846793005ULL + 1442695040888963407ULL; return x >> 11; }
+static float urand(unsigned long long& x, float lo, float hi) { return lo + (hi - lo) * (float)((double)lcg(x) / 9007199254740992.0); }
+extern "C" int fm_emu_check_box_on_face(int n, unsigned long long seed, int* applied) {
+  int bad = 0; *applied = 0;
+  for (int it = 0; it < n; ++it) {
+    f3 hb = (it & 1) ? mk3(0.3f, 100.f, 0.04f) : ((it & 2) ? mk3(1.2f, 1.0f, 0.5f) : mk3(0.29f, 0.29f, 0.02f));
+    f3 pb = mk3(urand(seed, -1, 1), urand(seed, -1, 1), urand(seed, 0.5f, 1.5f));
+    float h = urand(seed, 0.03f, 0.05f); f3 hc = mk3(h, h, h);
+    q4 q = qnormf(mkq(urand(seed, -1, 1), urand(seed, -1, 1), urand(seed, -1, 1), urand(seed, -1, 1)));
+    if (it % 5 == 0) q = qnormf(mkq(1.f, urand(seed, -1e-3f, 1e-3f), urand(seed, -1e-3f, 1e-3f), urand(seed, -1, 1)));   // nearly flat
+    if (it % 7 == 0) q = qnormf(mkq(urand(seed, -1, 1), 0, 0, urand(seed, -1, 1)));                                     // exactly flat, yawed
+    float Rc[9]; q2matf(q, Rc);
+    float top = pb.z + hb.z;
+    f3 pc = mk3(pb.x + urand(seed, -hb.x, hb.x) * 0.9f, pb.y + urand(seed, -1.f, 1.f) * fminf(hb.y, 1.5f), top + urand(seed, -0.01f, 0.1f));
+    float Rid[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int order = 0; order < 1; ++order) {   // the kernel uses the fast path only with the big box as geom1
+      RawC a[8], b[8];
+      int nf = col_box_on_face(pb, hb, pc, Rc, hc, order == 0, a);
+      if (nf < 0) continue;
+      (*applied)++;
+      int ng = order == 0 ? col_box_box(pb, Rid, hb, pc, Rc, hc, b) : col_box_box(pc, Rc, hc, pb, Rid, hb, b);
+      bool ok = nf == ng;
+      for (int k = 0; ok && k < nf; ++k)
+        ok = fabsf(a[k].pos.x - b[k].pos.x) < 2e-6f && fabsf(a[k].pos.y - b[k].pos.y) < 2e-6f && fabsf(a[k].pos.z - b[k].pos.z) < 2e-6f &&
+             fabsf(a[k].dist - b[k].dist) < 2e-6f && fabsf(a[k].n.z - b[k].n.z) < 1e-6f;
+      if (!ok) bad++;
+    }
+  }
+  return bad;
+}
 extern "C" {
 void fm_emu_set_order(int o) { g_order = o; }
 void fm_emu_counters(long long* o) { o[0] = fm_dbg_sweeps; o[1] = fm_dbg_visits; o[2] = fm_dbg_islands; }
@@ -56,7 +88,7 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
-    h->E = (h->hm.n_arms == 2 && cfg->envs_per_block == 8) ? 8 : 4;
+    h->E = (cfg->envs_per_block == 1 || cfg->envs_per_block == 2) ? cfg->envs_per_block : 4;
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs};
     *out = h; return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }

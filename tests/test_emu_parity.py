@@ -83,3 +83,13 @@ def test_no_intra_interval_dependencies():
     for r in outs[1:]:
         for x, y in zip(outs[0], r):
             assert np.array_equal(x, y)
+
+
+def test_box_on_face_fast_path_equals_general_box_box():
+    """200k random cube poses over belt / table / bucket-floor sized boxes: the fast path of the narrow phase returns the
+    same contacts (count, order, position, depth) as the general separating-axis routine whenever it applies."""
+    import ctypes as C
+    from tests.emu_backend import emu_lib
+    applied = C.c_int()
+    bad = emu_lib().fm_emu_check_box_on_face(200000, C.c_ulonglong(2024), C.byref(applied))
+    assert applied.value > 100000 and bad == 0, (bad, applied.value)
