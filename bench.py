@@ -31,6 +31,9 @@ METRIC = "batched TaskEnv env-steps/sec"
 UNIT = "env-steps/s"
 # algorithmic work per env-step (DESIGN.md "Measurement"): state in+out + action + obs + scalars, fp32 flop hand count
 FLOP_PER_ENV_STEP = 2.1e7
+# dram__bytes_read.sum + dram__bytes_write.sum of fm_step_kernel per env, from the ncu --set full capture profiles/r1e_step_kernel_ncu_raw.csv
+# (6.13 MB per launch of 1184 envs); the launch at bench size was not captured separately
+DRAM_BYTES_PER_ENV_NCU = 6.13e6 / 1184
 
 
 def peaks():
@@ -150,7 +153,8 @@ def run_ours(args):
         o2, rew, term, _ = env.step(act)
         return o2
 
-    for _ in range(W):
+    # untimed pre-roll into the steady state of an episode (first cube riding the belt, hidden cubes settled), then W warm-up steps
+    for _ in range(args.preroll + W):
         obs = one_step(obs)
     torch.cuda.synchronize()
     l0 = env.gpu_launches + pol.launches
@@ -234,8 +238,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{n} batched TaskEnv per GPU ({ENV_CLASS} action map), two arms, fixed random policy (178-128-128-16 tanh MLP, seed 0), 100 sub-steps per step",
-                           "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB write)", "pgs": [env.core.cfg.pgs_outer, env.core.cfg.pgs_inner]},
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                           "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB write)", "preroll_steps": args.preroll,
+                           "solver": "PGS, adaptive (<= 8 sweeps, tol 1e-3 m/s^2), forces persisted across sub-steps; resting hidden cubes asleep"},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": DRAM_BYTES_PER_ENV_NCU * n,
                              "peak_source": peak_kind, "kernel": "fm_step_kernel", "kernel_ms": kern_ms, "bytes_per_env_step": bytes_per_env,
                              "note": "the step kernel is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); see roofline_fp32"},
                 "roofline_fp32": {"achieved": FLOP_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -264,6 +269,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--ppo-steps", type=int, default=8)
+    ap.add_argument("--preroll", type=int, default=60)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
