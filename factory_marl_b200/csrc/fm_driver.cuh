@@ -31,12 +31,34 @@ struct FmStepArgs {
 };
 
 template <int NA, int E, class Run>
+FM_HD void fm_arm_kinematics(Run& run, EnvS<NA>* S, const FmDevModel& m, int T) {
+  run([&](int tid) { ph_arm_local<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 1, true); });
+  run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 2, false); });
+  run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 4, true); });
+  run([&](int tid) { ph_arm_plates<NA, E>(S, tid, T); });
+}
+
+template <int NA, int E, class Run>
 FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class, int T, int sleep_hidden) {
-  run([&](int tid) { ph_clear<NA, E>(S, tid, T); ph_cube_derive<NA, E>(S, m, tid, T, sleep_hidden); ph_arm_fk<NA, E>(S, m, tid, T, true); });
+  run([&](int tid) { ph_clear<NA, E>(S, tid, T); ph_cube_derive<NA, E>(S, m, tid, T, sleep_hidden); ph_arm_local<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 1, true); });
+  run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 2, false); });
+  run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 4, true); });
+  run([&](int tid) { ph_arm_plates<NA, E>(S, tid, T); });
+  run([&](int tid) { ph_arm_vel<NA, E>(S, m, tid, T); });
   run([&](int tid) { ph_arm_body<NA, E>(S, m, tid, T); });
-  run([&](int tid) { ph_arm_backward<NA, E>(S, m, tid, T); ph_broad<NA, E>(S, m, cpairs, tid, T); });
+  run([&](int tid) { ph_arm_bwd<NA, E>(S, tid, T); ph_broad<NA, E>(S, m, cpairs, tid, T); });
   run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); });
-  run([&](int tid) { ph_arm_chol<NA, E>(S, m, tid, T); ph_narrow<NA, E>(S, m, cpairs, tid, T); });   // raw contacts reuse the arm scratch
+  run([&](int tid) { ph_arm_chol_col<NA, E, 0>(S, tid, T); ph_narrow<NA, E>(S, m, cpairs, tid, T); });   // raw contacts reuse the arm scratch
+  run([&](int tid) { ph_arm_chol_col<NA, E, 1>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 2>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 3>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 4>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 5>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 6>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 7>(S, tid, T); });
+  run([&](int tid) { ph_arm_chol_col<NA, E, 8>(S, tid, T); });
   run([&](int tid) { ph_arm_minv<NA, E>(S, tid, T); });
   run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T); ph_arm_rows<NA, E>(S, m, tid, T); });
 }
@@ -50,7 +72,7 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
   if (stage == 0) {
     d->ncon = s.ncon; d->nqueue = s.nqueue; d->flags = s.flags;
     for (int c = 0; c < s.ncon && c < FM_MAXCON; ++c) {
-      d->c_g[c] = s.c_g[c];
+      d->c_g[c] = ((s.c_key[c] >> 13) << 12) | ((s.c_key[c] >> 4) & 511);
       for (int k = 0; k < 3; ++k) { d->c_p[c][k] = s.c_p[c][k]; d->c_n[c][k] = s.c_n[c][k]; }
     }
     for (int a = 0; a < NA; ++a) {
@@ -84,7 +106,7 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
         if (doit) task_reset_state(S[w], TS[w], cfg);
       }
     });
-    run([&](int tid) { ph_arm_fk<NA, E>(S, m, tid, T, false); });
+    fm_arm_kinematics<NA, E>(run, S, m, T);
     run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, tid, T, true); });
     run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
     return;
@@ -115,7 +137,8 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
     return;
   }
   // kinematics of the final state for the gripper sites (reward / IK policy read site_xpos after the last mj_step1)
-  run([&](int tid) { ph_arm_fk<NA, E>(S, m, tid, T, false); ph_store_pre<NA, E>(S, st, env0, tid, T); });
+  run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, tid, T); });
+  fm_arm_kinematics<NA, E>(run, S, m, T);
   run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); });
   run([&](int tid) { ph_task<NA, E>(S, TS, m, cfg, st, env0, tid, T); });
   run([&](int tid) { ph_obs<NA, E>(S, TS, ar.terminal_obs, obs_dim, st.n, env0, tid, T, true); ph_outputs<NA, E>(S, TS, st, ar.reward, ar.terminated, ar.scores, ar.flags, ar.ep_info, env0, tid, T); });

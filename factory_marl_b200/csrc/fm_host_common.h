@@ -15,7 +15,7 @@ inline FmEnvCfg fm_make_cfg(const fm_config& c, double h) {
   e.frame_skip = (int)((1.0 / c.control_frequency) / h);                 // base_env.py:134
   e.dt = h * e.frame_skip;                                               // base_env.py:201
   e.pgs_outer = c.pgs_outer > 0 ? c.pgs_outer : 2;
-  e.pgs_inner = c.pgs_inner > 0 ? c.pgs_inner : 8;
+  e.pgs_inner = c.pgs_inner > 0 ? c.pgs_inner : 4;
   e.sleep_hidden = c.reserved == 0 ? 1 : 0;          // fm_config.reserved: 0 = sleep resting hidden cubes (default), 1 = keep them live
   e.pgs_tol = c.pgs_tol > 0 ? c.pgs_tol : 1e-3f;      // m/s^2: below the fp32 noise floor of the stiff rows
   e.initial_conveyor_speed = c.initial_conveyor_speed; e.conveyor_acceleration = c.conveyor_acceleration;

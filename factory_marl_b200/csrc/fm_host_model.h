@@ -62,7 +62,7 @@ inline void fm_build_host_model(const void* blob, size_t n, FmHostModel& H) {
   const int32_t* cg = I(blob, n, "g_cube_geom");
   for (int k = 0; k < FM_NCUBE; ++k) {
     m.cube_half[k] = (float)cu[4 * k]; m.cube_mass[k] = (float)cu[4 * k + 1]; m.cube_inertia[k] = (float)cu[4 * k + 2]; m.cube_invw[k] = (float)cu[4 * k + 3];
-    m.cube_geom[k] = cg[k];
+    m.cube_geom[k] = cg[k]; m.cube_invm[k] = (float)(1.0 / cu[4 * k + 1]); m.cube_invI[k] = (float)(1.0 / cu[4 * k + 2]);
   }
   m.cube_class = gclass[cg[0]]; m.floor_class = gclass[0];
   const double* pp = D(blob, n, "g_pair_param", &c);

@@ -48,7 +48,7 @@ struct fm_handle {
   FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st;
   int E = 4; size_t smem = 0;
   FmDevModel* d_model = nullptr; FmIkModel* d_ik = nullptr; unsigned int* d_cpairs = nullptr; int* d_geom_class = nullptr;
-  FmDebugDump* d_dump = nullptr;
+  FmDebugDump* d_dump = nullptr; float* d_ws = nullptr;
   long long launches = 0;
 };
 
@@ -67,11 +67,9 @@ static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
   if (h->hm.n_arms == 2) {
     if (h->E == 1) return launch_step<2, 1>(h, ar, s);
-    if (h->E == 2) return launch_step<2, 2>(h, ar, s);
     return launch_step<2, 4>(h, ar, s);
   }
   if (h->E == 1) return launch_step<4, 1>(h, ar, s);
-  if (h->E == 2) return launch_step<4, 2>(h, ar, s);
   return launch_step<4, 4>(h, ar, s);
 }
 
@@ -89,8 +87,8 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (cfg->env_class < 0 || cfg->env_class > 6) throw std::runtime_error("bad env_class");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
     int E = cfg->envs_per_block;
-    h->E = (E == 1 || E == 2 || E == 4) ? E : FM_DEFAULT_E;
-    h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs};
+    h->E = (E == 1 || E == 4) ? E : FM_DEFAULT_E;
+    h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, nullptr};
     FM_CUDA(cudaMalloc(&h->d_model, sizeof(FmDevModel)));
     FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_ik, sizeof(FmIkModel)));
@@ -100,13 +98,16 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     FM_CUDA(cudaMalloc(&h->d_geom_class, h->hm.geom_class.size() * sizeof(int)));
     FM_CUDA(cudaMemcpy(h->d_geom_class, h->hm.geom_class.data(), h->hm.geom_class.size() * sizeof(int), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_dump, sizeof(FmDebugDump)));
+    FM_CUDA(cudaMalloc(&h->d_ws, (size_t)cfg->n_envs * FM_WS_FLOATS * sizeof(float)));
+    FM_CUDA(cudaMemset(h->d_ws, 0, (size_t)cfg->n_envs * FM_WS_FLOATS * sizeof(float)));
+    h->st.ws = h->d_ws;
     *out = h;
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 int fm_destroy(fm_handle* h) {
   if (!h) return 0;
-  cudaFree(h->d_model); cudaFree(h->d_ik); cudaFree(h->d_cpairs); cudaFree(h->d_geom_class); cudaFree(h->d_dump);
+  cudaFree(h->d_model); cudaFree(h->d_ik); cudaFree(h->d_cpairs); cudaFree(h->d_geom_class); cudaFree(h->d_dump); cudaFree(h->d_ws);
   delete h; return 0;
 }
 int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : Lay<4>::obs_dim(h->cfg.env_class); }

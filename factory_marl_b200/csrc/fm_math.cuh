@@ -13,6 +13,10 @@
 #define FM_D static inline
 #endif
 
+#if !defined(__CUDACC__)
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline void sincosf_host(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+#endif
 struct f3 { float x, y, z; };
 FM_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 FM_HD f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }

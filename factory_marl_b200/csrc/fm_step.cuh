@@ -46,6 +46,12 @@ static long long fm_dbg_sweeps = 0, fm_dbg_visits = 0, fm_dbg_islands = 0;   // 
 #define FM_ASSUME_SHARED(p)
 #define FM_ASSUME_GLOBAL(p)
 #endif
+#if defined(__CUDA_ARCH__)
+#define FM_FDIV(a, b) __fdividef((a), (b))
+#else
+#define FM_FDIV(a, b) ((a) / (b))
+#endif
+#define FM_WS_FLOATS (FM_MAXARMSIDE * 54 + FM_MAXCON * 4)   // per-env global scratch: as_J, as_B, prev_f
 #define FM_QMAX 96
 #define FM_AROW 10   // equality + up to 9 limit rows per arm
 
@@ -67,7 +73,7 @@ struct EnvS {
   float body_x[NA][FM_NARMBODY][3], body_R[NA][FM_NARMBODY][9];
   alignas(16) float bnd[FM_NCUBE + NA * FM_NARMBODY][4];   // bounding spheres (x, y, z, r) of the cube / arm-body clusters
   float M[NA][45], Minv[NA][81], Li[NA][45], Lc[NA][45];
-  float bias[NA][9];
+  float bias[NA][9], chol_d[NA][2][9];      // chol_d: diagonal of the Cholesky factors of M (0) and M - hD (1)
   // ---- acceleration stage
   float acc[NV];
   float belt_acc_smooth, belt_S;
@@ -77,10 +83,12 @@ struct EnvS {
   float arow_aref[NA][FM_AROW], arow_R[NA][FM_AROW], arow_f[NA][FM_AROW];
   // ---- contacts
   int ncon, nraw, n_armside, flags, nqueue;
-  int c_side[FM_MAXCON], c_g[FM_MAXCON];
-  float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_mu[FM_MAXCON], c_R[FM_MAXCON], c_W[FM_MAXCON][6];
+  int c_side[FM_MAXCON];
+  float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_t1[FM_MAXCON][3], c_mu[FM_MAXCON], c_R[FM_MAXCON], c_W[FM_MAXCON][6];
   float c_aref[FM_MAXCON][4], c_f[FM_MAXCON][4];
-  float as_J[FM_MAXARMSIDE][27], as_B[FM_MAXARMSIDE][27];
+  // rarely / once-per-sub-step touched buffers live in a library-owned global scratch row of this env (L2-resident; see
+  // FM_WS_FLOATS): arm-side Jacobians (3x9) and Minv J^T of contacts that touch an arm, and the previous solve's contact forces
+  float (*as_J)[27]; float (*as_B)[27]; float (*prev_f)[4];
   int isl_root[NNODE], isl_start[NNODE + 1], need_union;
   unsigned char isl_list[FM_MAXCON], c_node[FM_MAXCON];
   unsigned short queue[FM_QMAX];
@@ -88,9 +96,16 @@ struct EnvS {
   //      ph_narrow, which the schedule runs after ph_arm_M, and dead after ph_contact_setup)
   union {
     struct {
-      float d_c[NA][FM_NARMBODY][3], d_Ic[NA][FM_NARMBODY][6], d_comp[NA][FM_NARMBODY][10];
-      float d_om[NA][FM_NARMBODY][3], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3];
-      float d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3];
+      float d_c[NA][FM_NARMBODY][3];
+      union {
+        struct { float d_comp0[NA][FM_NARMBODY][10], d_comp[NA][FM_NARMBODY][10]; };   // body phase onwards: own / composite inertia
+        struct { float d_L[NA][FM_NARMBODY][9], d_p[NA][FM_NARMBODY][3]; };           // FK scan ping-pong buffer (dead after the scan)
+      };
+      union {
+        struct { float d_om[NA][FM_NARMBODY][3], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3]; };   // until ph_arm_body
+        struct { float d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3]; };                               // accumulated wrench (ph_arm_bwd)
+      };
+      float d_f0[NA][FM_NARMBODY][3], d_n0[NA][FM_NARMBODY][3];                                           // own wrench (ph_arm_body)
     };
     struct {
       int raw_key[FM_MAXCON], raw_g[FM_MAXCON];
@@ -100,7 +115,6 @@ struct EnvS {
   float force_max;
   // forces of the previous solve, keyed by contact identity (warm start of the dual; persisted in HBM between env steps)
   int prev_n, prev_key[FM_MAXCON];
-  float prev_f[FM_MAXCON][4];
   int prev_arow_n[NA], prev_arow_code[NA][FM_AROW];
   float prev_arow_f[NA][FM_AROW];
   int c_key[FM_MAXCON];
@@ -159,56 +173,98 @@ FM_HD void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int 
   }
 }
 
-// phase: arm forward kinematics + Newton-Euler forward recursion (angular velocity, bias accelerations).
-// One thread per (env, arm); world-aligned axes, link-origin reference points.
+// ---------------------------------------------------------------------------------------------------------------------
+// Arm kinematics + Newton-Euler forward pass, lane-parallel (work item = (env, arm, body)):
+//   local transforms -> prefix products by a 3-round scan over the 8-body chain (+ the two plates) -> angular velocity,
+//   angular and linear bias accelerations as prefix sums of per-link terms.  World-aligned axes, link-origin reference
+//   points.  Every function below is one barrier interval (cheap with one warp per env).
+template <int NA>
+FM_HD void xf_compose(const float* Ra, const float* xa, const float* Rb, const float* xb, float* Ro, float* xo) {
+  float R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = Ra[3 * i] * Rb[j] + Ra[3 * i + 1] * Rb[3 + j] + Ra[3 * i + 2] * Rb[6 + j];
+  f3 x = ld3(xa) + rmul(Ra, ld3(xb));
+  for (int i = 0; i < 9; ++i) Ro[i] = R[i];
+  st3(xo, x);
+}
 template <int NA, int E>
-FM_HD void ph_arm_fk(EnvS<NA>* S, const FmDevModel& m, int tid, int T, bool with_vel) {
+FM_HD void ph_arm_local(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-  for (int w = tid; w < NA * E; w += T) {
-    EnvS<NA>& s = S[w % E]; int a = w / E;
-    // rotation matrices are propagated directly: R_b = R_parent * C_b * Rz(q_b) with the constant body rotation C_b
-    // (iiwa14.xml frame quats) precomputed by the host; a hinge only mixes the first two columns.
-    f3 x = ld3(m.arm_base_pos[a]);
-    float Rp[9];
-    for (int i = 0; i < 9; ++i) { Rp[i] = m.arm_base_R[a][i]; s.body_R[a][0][i] = Rp[i]; }
-    st3(s.body_x[a][0], x);
-    f3 om = mk3(0, 0, 0), al = mk3(0, 0, 0), ap = mk3(0, 0, m.g);
-    if (with_vel) { st3(s.d_om[a][0], om); st3(s.d_al[a][0], al); st3(s.d_ap[a][0], ap); }
-    f3 x8 = x, om8 = om, al8 = al, ap8 = ap; float R8[9];
-    for (int b = 1; b < FM_NARMBODY; ++b) {
-      if (b >= 9) { x = x8; om = om8; al = al8; ap = ap8; for (int i = 0; i < 9; ++i) Rp[i] = R8[i]; }
-      f3 r = rmul(Rp, ld3(m.ab_pos[b]));
-      const float* Cb = m.ab_C[b];
-      float R[9];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) R[3 * i + j] = Rp[3 * i] * Cb[j] + Rp[3 * i + 1] * Cb[3 + j] + Rp[3 * i + 2] * Cb[6 + j];
-      int d = ab_dof(b);
-      f3 axv = mk3(0, 0, 0);
-      if (m.ab_jtype[b] == 1) {
-        float sn, cs;
-        sincosf(s.arm_q[a][d], &sn, &cs);
-        for (int i = 0; i < 3; ++i) { float c0 = R[3 * i], c1 = R[3 * i + 1]; R[3 * i] = cs * c0 + sn * c1; R[3 * i + 1] = cs * c1 - sn * c0; }
-        if (with_vel) axv = rcol(R, 2) * s.arm_v[a][d];
-      } else if (m.ab_jtype[b] == 2) {
-        f3 ax = rcol(R, 0);
-        r = r + ax * s.arm_q[a][d];
-        if (with_vel) axv = ax * s.arm_v[a][d];
-      }
-      if (with_vel) {
-        // acceleration of the new origin (bias part, qacc = 0), then angular quantities
-        ap = ap + cross3(al, r) + cross3(om, cross3(om, r));
-        if (m.ab_jtype[b] == 1) { al = al + cross3(om, axv); om = om + axv; }
-        else if (m.ab_jtype[b] == 2) { ap = ap + 2.0f * cross3(om, axv); }
-        st3(s.d_om[a][b], om); st3(s.d_al[a][b], al); st3(s.d_ap[a][b], ap);
-      }
-      x = x + r;
-      st3(s.body_x[a][b], x);
-      for (int i = 0; i < 9; ++i) { s.body_R[a][b][i] = R[i]; Rp[i] = R[i]; }
-      if (b == 8) { x8 = x; om8 = om; al8 = al; ap8 = ap; for (int i = 0; i < 9; ++i) R8[i] = R[i]; }
+  for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
+    if (b == 0) {   // static base body
+      for (int i = 0; i < 9; ++i) s.body_R[a][0][i] = m.arm_base_R[a][i];
+      st3(s.body_x[a][0], ld3(m.arm_base_pos[a]));
+      continue;
     }
+    float R[9];
+    for (int i = 0; i < 9; ++i) R[i] = m.ab_C[b][i];
+    f3 p = ld3(m.ab_pos[b]);
+    int d = ab_dof(b);
+    if (m.ab_jtype[b] == 1) {
+      float sn, cs; sincosf(s.arm_q[a][d], &sn, &cs);
+      for (int i = 0; i < 3; ++i) { float c0 = R[3 * i], c1 = R[3 * i + 1]; R[3 * i] = cs * c0 + sn * c1; R[3 * i + 1] = cs * c1 - sn * c0; }
+    } else if (m.ab_jtype[b] == 2) p = p + rcol(R, 0) * s.arm_q[a][d];
+    if (b == 1) {   // fold the base frame into the first link
+      float xb[3]; st3(xb, p);
+      xf_compose<NA>(m.arm_base_R[a], m.arm_base_pos[a], R, xb, s.d_L[a][1], s.d_p[a][1]);
+    } else { for (int i = 0; i < 9; ++i) s.d_L[a][b][i] = R[i]; st3(s.d_p[a][b], p); }
   }
 }
-
+// one scan round: dst_b = (b - dist >= 1 ? src_{b-dist} o src_b : src_b) for chain bodies 1..8; plates are carried through
+template <int NA, int E>
+FM_HD void ph_arm_scan(EnvS<NA>* S, int tid, int T, int dist, bool to_body) {
+  FM_ASSUME_SHARED(S);
+  for (int w = tid; w < NA * (FM_NARMBODY - 1) * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / (FM_NARMBODY - 1), b = 1 + ab % (FM_NARMBODY - 1);
+    const float *sR = to_body ? s.d_L[a][b] : s.body_R[a][b], *sx = to_body ? s.d_p[a][b] : s.body_x[a][b];
+    float *dR = to_body ? s.body_R[a][b] : s.d_L[a][b], *dx = to_body ? s.body_x[a][b] : s.d_p[a][b];
+    if (b <= 8 && b - dist >= 1) {
+      const float *pR = to_body ? s.d_L[a][b - dist] : s.body_R[a][b - dist], *px = to_body ? s.d_p[a][b - dist] : s.body_x[a][b - dist];
+      xf_compose<NA>(pR, px, sR, sx, dR, dx);
+    } else { for (int i = 0; i < 9; ++i) dR[i] = sR[i]; for (int i = 0; i < 3; ++i) dx[i] = sx[i]; }
+  }
+}
+// plates: world frame = gripper_base frame o local; reads the plates' local transforms from d_L and writes body_R/body_x.
+// After the rounds (dist 1 -> body, 2 -> d_L, 4 -> body) bodies 1..8 are final in body_R and the plates' locals sit in body_R
+// as well (carried), so they are first copied back by the caller's last round; here they are composed in place via registers.
+template <int NA, int E>
+FM_HD void ph_arm_plates(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
+  for (int w = tid; w < NA * 2 * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ap = w / E; int a = ap / 2, b = 9 + ap % 2;
+    float R[9], x[3];
+    xf_compose<NA>(s.body_R[a][8], s.body_x[a][8], s.body_R[a][b], s.body_x[a][b], R, x);
+    for (int i = 0; i < 9; ++i) s.body_R[a][b][i] = R[i];
+    for (int i = 0; i < 3; ++i) s.body_x[a][b][i] = x[i];
+  }
+}
+// chain membership: dof-carrying ancestors-or-self of body b are bodies 1..min(b,7) plus b itself for a plate
+FM_HD int chain_hi(int b) { return b < 7 ? b : 7; }
+// Newton-Euler forward pass in ONE interval: lane = (env, arm, body) walks its own ancestor chain with running angular
+// velocity, angular bias acceleration and origin bias acceleration (no cross-lane dependency; <= 8 links).
+template <int NA, int E>
+FM_HD void ph_arm_vel(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
+  for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
+    f3 om = mk3(0, 0, 0), al = mk3(0, 0, 0), ap = mk3(0, 0, m.g);
+    int hi = b <= 8 ? b : 8;
+    f3 xp = ld3(s.body_x[a][0]);
+    for (int i = 1; i <= hi; ++i) {
+      f3 xi = ld3(s.body_x[a][i]);
+      f3 r = xi - xp; xp = xi;
+      ap = ap + cross3(al, r) + cross3(om, cross3(om, r));
+      if (i <= 7) { f3 t = rcol(s.body_R[a][i], 2) * s.arm_v[a][i - 1]; al = al + cross3(om, t); om = om + t; }
+    }
+    if (b >= 9) {
+      f3 r = ld3(s.body_x[a][b]) - xp;
+      ap = ap + cross3(al, r) + cross3(om, cross3(om, r)) + 2.0f * cross3(om, rcol(s.body_R[a][b], 0) * s.arm_v[a][b - 2]);
+    }
+    st3(s.d_om[a][b], om); st3(s.d_al[a][b], al); st3(s.d_ap[a][b], ap);
+  }
+}
+// final kinematics only (gripper sites after the last sub-step): same scan without the velocity passes
 // phase: per-body quantities (parallel): COM offset, world inertia, composite init, NE body wrench, cluster centre
 template <int NA, int E>
 FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
@@ -237,9 +293,8 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
     Iw[4] = T1[0] * R[6] + T1[1] * R[7] + T1[2] * R[8];
     Iw[5] = T1[3] * R[6] + T1[4] * R[7] + T1[5] * R[8];
     st3(s.d_c[a][b], c);
-    for (int i = 0; i < 6; ++i) s.d_Ic[a][b][i] = Iw[i];
     float cc = dot3(c, c);
-    float* cp = s.d_comp[a][b];
+    float* cp = s.d_comp0[a][b];
     cp[0] = ms; cp[1] = ms * c.x; cp[2] = ms * c.y; cp[3] = ms * c.z;
     cp[4] = Iw[0] + ms * (cc - c.x * c.x); cp[5] = Iw[1] + ms * (cc - c.y * c.y); cp[6] = Iw[2] + ms * (cc - c.z * c.z);
     cp[7] = Iw[3] - ms * c.x * c.y; cp[8] = Iw[4] - ms * c.x * c.z; cp[9] = Iw[5] - ms * c.y * c.z;
@@ -248,23 +303,28 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
     f3 ac = ap + cross3(al, c) + cross3(om, cross3(om, c));
     f3 f = ac * ms;
     f3 n = symmul6(Iw, al) + cross3(om, symmul6(Iw, om)) + cross3(c, f);
-    st3(s.d_f[a][b], f); st3(s.d_n[a][b], n);
+    st3(s.d_f0[a][b], f); st3(s.d_n0[a][b], n);
   }
 }
 
-// phase: backward recursions (thread per arm): composite inertias about body origins, NE wrench accumulation, bias
+// phase: composite inertias and accumulated Newton-Euler wrenches as direct sums over each body's descendants
+// (lane = (env, arm, body); subtree of chain body b is b+1..10, of the gripper base the two plates).  Reads the per-body
+// values written by ph_arm_body (d_comp0, d_f0, d_n0) and writes the accumulated ones (d_comp, d_f, d_n): one interval.
 template <int NA, int E>
-FM_HD void ph_arm_backward(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
-  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-  for (int w = tid; w < NA * E; w += T) {
-    EnvS<NA>& s = S[w % E]; int a = w / E;
-    for (int b = FM_NARMBODY - 1; b >= 2; --b) {
-      int p = ab_parent(b);
-      f3 r = ld3(s.body_x[a][b]) - ld3(s.body_x[a][p]);
-      const float* cc = s.d_comp[a][b]; float* cp = s.d_comp[a][p];
+FM_HD void ph_arm_bwd(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
+  for (int w = tid; w < NA * (FM_NARMBODY - 1) * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / (FM_NARMBODY - 1), b = 1 + ab % (FM_NARMBODY - 1);
+    float cp[10];
+    for (int k = 0; k < 10; ++k) cp[k] = s.d_comp0[a][b][k];
+    f3 F = ld3(s.d_f0[a][b]), Nn = ld3(s.d_n0[a][b]);
+    f3 xb = ld3(s.body_x[a][b]);
+    int d_hi = b <= 8 ? FM_NARMBODY - 1 : b;      // plates are leaves
+    for (int d = b + 1; d <= d_hi; ++d) {
+      f3 r = ld3(s.body_x[a][d]) - xb;
+      const float* cc = s.d_comp0[a][d];
       float ms = cc[0]; f3 hh = mk3(cc[1], cc[2], cc[3]);
-      float rr = dot3(r, r), rh = dot3(r, hh);
-      float dg = ms * rr + 2.0f * rh;
+      float dg = ms * dot3(r, r) + 2.0f * dot3(r, hh);
       cp[0] += ms; cp[1] += hh.x + ms * r.x; cp[2] += hh.y + ms * r.y; cp[3] += hh.z + ms * r.z;
       cp[4] += cc[4] + dg - (ms * r.x * r.x + 2.0f * r.x * hh.x);
       cp[5] += cc[5] + dg - (ms * r.y * r.y + 2.0f * r.y * hh.y);
@@ -272,16 +332,11 @@ FM_HD void ph_arm_backward(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       cp[7] += cc[7] - (ms * r.x * r.y + r.x * hh.y + hh.x * r.y);
       cp[8] += cc[8] - (ms * r.x * r.z + r.x * hh.z + hh.x * r.z);
       cp[9] += cc[9] - (ms * r.y * r.z + r.y * hh.z + hh.y * r.z);
-      // wrench
-      f3 f = ld3(s.d_f[a][b]), n = ld3(s.d_n[a][b]);
-      st3(s.d_f[a][p], ld3(s.d_f[a][p]) + f);
-      st3(s.d_n[a][p], ld3(s.d_n[a][p]) + n + cross3(r, f));
+      f3 f = ld3(s.d_f0[a][d]);
+      F = F + f; Nn = Nn + ld3(s.d_n0[a][d]) + cross3(r, f);
     }
-    for (int d = 0; d < 9; ++d) {
-      int b = dof_body(d);
-      const float* R = s.body_R[a][b];
-      s.bias[a][d] = d < 7 ? dot3(rcol(R, 2), ld3(s.d_n[a][b])) : dot3(rcol(R, 0), ld3(s.d_f[a][b]));
-    }
+    for (int k = 0; k < 10; ++k) s.d_comp[a][b][k] = cp[k];
+    st3(s.d_f[a][b], F); st3(s.d_n[a][b], Nn);
   }
 }
 
@@ -309,53 +364,53 @@ FM_HD void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       }
     }
     s.M[a][pr] = val;
-  }
-}
-
-// phase: Cholesky factors (thread per arm): Lc = chol(M), Li = chol(M - h*D) with D = d(actuator force)/d(qvel) [3P implicitfast]
-template <int NA, int E>
-FM_HD void ph_arm_chol(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
-  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-  for (int w = tid; w < 2 * NA * E; w += T) {
-    EnvS<NA>& s = S[w % E]; int ai = w / E; int a = ai >> 1, which = ai & 1;
-    float L[45];
-#pragma unroll
-    for (int i = 0; i < 45; ++i) L[i] = s.M[a][i];
-    if (which) {
-      for (int d = 0; d < 7; ++d) L[tri(d, d)] += m.h * m.kd;
-      float gd = m.h * m.g_kd;   // gripper tendon actuator: moment^T * kd * moment (never force-clamped in range)
-      L[tri(7, 7)] += gd * m.ten0 * m.ten0; L[tri(8, 8)] += gd * m.ten1 * m.ten1; L[tri(8, 7)] += gd * m.ten0 * m.ten1;
+    // work copies for the two Cholesky factorisations: M and M - h*D (D = d(actuator force)/d(qvel), implicitfast [3P])
+    s.Lc[a][pr] = val;
+    float add = 0.f;
+    if (i == j && i < 7) add = m.h * m.kd;
+    else if (i >= 7 && j >= 7) { float gd = m.h * m.g_kd; add = gd * (i == 7 ? m.ten0 : m.ten1) * (j == 7 ? m.ten0 : m.ten1); }   // (7,7), (8,7), (8,8)
+    s.Li[a][pr] = val + add;
+    if (pr < 9) {   // bias force of dof `pr` from the accumulated wrench of its body
+      int bb = dof_body(pr);
+      const float* Rb = s.body_R[a][bb];
+      s.bias[a][pr] = pr < 7 ? dot3(rcol(Rb, 2), ld3(s.d_n[a][bb])) : dot3(rcol(Rb, 0), ld3(s.d_f[a][bb]));
     }
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        float sum = L[tri(i, j)];
-#pragma unroll
-        for (int k = 0; k < j; ++k) sum -= L[tri(i, k)] * L[tri(j, k)];
-        if (i == j) L[tri(i, i)] = sqrtf(fmaxf(sum, 1e-20f));
-        else L[tri(i, j)] = sum / L[tri(j, j)];
-      }
-    float* out = which ? s.Li[a] : s.Lc[a];
-#pragma unroll
-    for (int i = 0; i < 45; ++i) out[i] = L[i];
   }
 }
 
-FM_HD void chol9_solve(const float* L, float* x) {
+// phase: column k of the two Cholesky factors of every arm, lane = (env, arm, matrix, row i >= k), in place on Lc / Li.
+// L[i][k] = (A[i][k] - sum_{j<k} L[i][j] L[k][j]) / L[k][k]; the pivot is recomputed by every lane (k MACs), so an interval
+// has no intra-interval dependency.
+template <int NA, int E, int K>
+FM_HD void ph_arm_chol_col(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
+  constexpr int ROWS = 9 - K;
+  for (int w = tid; w < NA * 2 * ROWS * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int r = w / E; int i = K + r % ROWS, mw = r / ROWS; int a = mw >> 1, which = mw & 1;
+    float* L = which ? s.Li[a] : s.Lc[a];
+    float sk = L[tri(K, K)], si = L[tri(i, K)];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { float lkj = L[tri(K, j)]; sk -= lkj * lkj; si -= L[tri(i, j)] * lkj; }
+    float rp = rsqrtf(fmaxf(sk, 1e-20f));
+    // the diagonal lives in chol_d (the unfactored A[k][k] stays in L so that lanes i > k of this interval still read it)
+    if (i == K) s.chol_d[a][which][K] = sk * rp; else L[tri(i, K)] = si * rp;
+  }
+}
+
+FM_HD void chol9_solve(const float* L, const float* dg, float* x) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     float sum = x[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) sum -= L[tri(i, k)] * x[k];
-    x[i] = sum / L[tri(i, i)];
+    x[i] = sum / dg[i];
   }
 #pragma unroll
   for (int i = 8; i >= 0; --i) {
     float sum = x[i];
 #pragma unroll
     for (int k = i + 1; k < 9; ++k) sum -= L[tri(k, i)] * x[k];
-    x[i] = sum / L[tri(i, i)];
+    x[i] = sum / dg[i];
   }
 }
 
@@ -368,7 +423,7 @@ FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
     float x[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = i == c ? 1.f : 0.f;
-    chol9_solve(s.Lc[a], x);
+    chol9_solve(s.Lc[a], s.chol_d[a][0], x);
 #pragma unroll
     for (int i = 0; i < 9; ++i) s.Minv[a][9 * i + c] = x[i];
   }
@@ -574,7 +629,7 @@ FM_HD void side_prepare(const EnvS<NA>& s, const FmDevModel& m, int sd, float sg
   if (o.type == FM_SIDE_CUBE) {
     int k = o.idx;
     o.r = p - ld3(s.cube_x[k]);
-    o.invm = 1.0f / m.cube_mass[k]; o.invI = 1.0f / m.cube_inertia[k];
+    o.invm = m.cube_invm[k]; o.invI = m.cube_invI[k];
   } else if (o.type == FM_SIDE_BELT) {
     o.jb[0] = n.y; o.jb[1] = t1.y; o.jb[2] = t2.y;
   } else if (o.type == FM_SIDE_ARM) {
@@ -671,8 +726,7 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
       s.c_node[c] = (unsigned char)(n0 >= 0 ? n0 : (n1 >= 0 ? n1 : 255));
       if (n0 >= 0 && n1 >= 0 && n0 != n1) s.need_union = 1;
     }
-    s.c_g[c] = (g1 << 12) | g2;
-    st3(s.c_p[c], p); st3(s.c_n[c], n); s.c_mu[c] = mu;
+    st3(s.c_p[c], p); st3(s.c_n[c], n); st3(s.c_t1[c], t1); s.c_mu[c] = mu;
     float K, Bd, imp; impedance_f(pp + 1, pp + 3, dist, m.h, K, Bd, imp);
     float dA = invw * (1.f + mu * mu);
     float R0 = fmaxf(1e-15f, (1.f - imp) * dA / imp);
@@ -852,7 +906,7 @@ FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 template <int NA>
 FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool first, float& belt_sum) {
   int cs = s.c_side[c];
-  f3 p = ld3(s.c_p[c]), n = ld3(s.c_n[c]); f3 t1, t2; make_frame3(n, t1, t2);
+  f3 p = ld3(s.c_p[c]), n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); f3 t2 = cross3(n, t1);
   SideW A, B;
   side_prepare(s, m, cs & 8191, -1.f, p, n, t1, t2, A);
   side_prepare(s, m, (cs >> 13) & 8191, +1.f, p, n, t1, t2, B);
@@ -872,7 +926,7 @@ FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool first, f
       float Wnt = tq == 1 ? W[3] : W[4], Wtt = tq == 1 ? W[1] : W[2], Wtx = W[5];
       float AR = W[0] + 2.f * cf * Wnt + cf * cf * Wtt + R;
       float res = u[0] + cf * u[tq] - s.c_aref[c][r] + R * f[r];
-      float fn = fmaxf(0.f, f[r] - res / AR);
+      float fn = fmaxf(0.f, f[r] - FM_FDIV(res, AR));
       float df = fn - f[r];
       f[r] = fn;
       // contact-space acceleration update: u += W * (1, cf on tangent tq) * df
@@ -1014,7 +1068,7 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
         for (int k = 0; k < 9; ++k) sum += s.M[a][r >= k ? tri(r, k) : tri(k, r)] * acc[k];
         y[r] = sum;
       }
-      chol9_solve(s.Li[a], y);
+      chol9_solve(s.Li[a], s.chol_d[a][1], y);
       for (int r = 0; r < 9; ++r) { s.arm_v[a][r] += h * y[r]; s.arm_q[a][r] += h * s.arm_v[a][r]; }
     }
   }

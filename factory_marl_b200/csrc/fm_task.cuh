@@ -17,7 +17,7 @@ struct Lay {
                    F_PRE_Q = F_ACC_WS + 1, F_PRE_V = F_PRE_Q + 70, F_LAST_GD = F_PRE_V + 60, F_LAST_BD = F_LAST_GD + NA,
                    F_IK_ACT = F_LAST_BD + NA, F_LAST_ARM_ACT = F_IK_ACT + 8 * NA, F_IK_LAST_CTRL = F_LAST_ARM_ACT + 8 * NA,
                    F_IK_MOVE_START = F_IK_LAST_CTRL + 8 * NA, F_SITE = F_IK_MOVE_START + 3 * NA, F_EP_RET = F_SITE + 3 * NA,
-                   F_PREV_F = F_EP_RET + 1, F_PREV_AF = F_PREV_F + 4 * FM_MAXCON, NF = F_PREV_AF + FM_AROW * NA;
+                   F_PREV_F = F_EP_RET + 1, F_PREV_AF = F_PREV_F, NF = F_PREV_AF + FM_AROW * NA;
   // double fields
   static const int D_CONV = 0, D_SPAWN_FREQ = 1, D_PLAY_TIME = 2, ND = 3;
   // int fields
@@ -29,7 +29,7 @@ struct Lay {
   FM_HDM static int obs_dim(int env_class) { return NA * 24 + 130 + ((env_class == FM_ENV_PAUSE_TOGGLE || env_class == FM_ENV_BACKUP_TOGGLE) ? 8 * NA : 0); }
 };
 
-struct FmStatePtrs { float* f; double* d; int* i; unsigned long long* rng; int n; };
+struct FmStatePtrs { float* f; double* d; int* i; unsigned long long* rng; int n; float* ws; /* library-owned scratch [n][FM_WS_FLOATS] */ };
 
 // per-env task scratch kept in shared memory next to EnvS
 struct TaskS {
@@ -89,7 +89,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     else if (fidx < L::F_LAST_BD) TS[e].last_gd[fidx - L::F_LAST_GD] = v;
     else if (fidx < L::F_IK_ACT) TS[e].last_bd[fidx - L::F_LAST_BD] = v;
     else if (fidx == L::F_EP_RET) TS[e].ep_ret = v;
-    else if (fidx >= L::F_PREV_F && fidx < L::F_PREV_AF) (&s.prev_f[0][0])[fidx - L::F_PREV_F] = v;
+    else if (fidx >= L::F_PREV_F && fidx < L::F_PREV_AF) { }   // contact forces persist in the library scratch (st.ws)
     else if (fidx >= L::F_PREV_AF) (&s.prev_arow_f[0][0])[fidx - L::F_PREV_AF] = v;
   }
   for (int w = tid; w < L::NI * E; w += T) {
@@ -118,6 +118,10 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     TS[w].play_time = st.d[(size_t)L::D_PLAY_TIME * N + env];
     S[w].conveyor_speed = (float)TS[w].conveyor_speed;
     S[w].flags = 0; S[w].force_max = 0.f;
+    float* ws = st.ws + (size_t)env * FM_WS_FLOATS;
+    S[w].as_J = reinterpret_cast<float (*)[27]>(ws);
+    S[w].as_B = reinterpret_cast<float (*)[27]>(ws + FM_MAXARMSIDE * 27);
+    S[w].prev_f = reinterpret_cast<float (*)[4]>(ws + FM_MAXARMSIDE * 54);
   }
 }
 
@@ -412,7 +416,7 @@ FM_HD void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
     }
     else if (fidx >= L::F_SITE && fidx < L::F_EP_RET) v = (&TS[e].site[0][0])[fidx - L::F_SITE];
     else if (fidx == L::F_EP_RET) v = TS[e].ep_ret;
-    else if (fidx >= L::F_PREV_F && fidx < L::F_PREV_AF) v = (&s.prev_f[0][0])[fidx - L::F_PREV_F];
+    else if (fidx >= L::F_PREV_F && fidx < L::F_PREV_AF) wr = false;
     else if (fidx >= L::F_PREV_AF) v = (&s.prev_arow_f[0][0])[fidx - L::F_PREV_AF];
     else wr = false;
     if (wr) st.f[(size_t)fidx * N + env] = v;

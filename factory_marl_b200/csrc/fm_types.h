@@ -29,7 +29,7 @@ struct FmDevModel {
   float belt_pos[3], belt_half[3], belt_mass, belt_damp, belt_kv, belt_invw;
   int belt_geom, belt_class;
   // cubes (scene.py:9-23,121-134)
-  float cube_half[FM_NCUBE], cube_mass[FM_NCUBE], cube_inertia[FM_NCUBE], cube_invw[FM_NCUBE];
+  float cube_half[FM_NCUBE], cube_mass[FM_NCUBE], cube_inertia[FM_NCUBE], cube_invw[FM_NCUBE], cube_invm[FM_NCUBE], cube_invI[FM_NCUBE];
   int cube_geom[FM_NCUBE], cube_class;
   int floor_class;
   // pair contact parameters by class: mu, solref0, solref1, solimp[5]

@@ -26,7 +26,7 @@ struct HostRun {
 
 struct fm_handle {
   FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st; int E;
-  std::vector<char> smem;
+  std::vector<char> smem; std::vector<float> ws;
 };
 
 template <int NA, int E>
@@ -89,7 +89,8 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
     h->E = (cfg->envs_per_block == 1 || cfg->envs_per_block == 2) ? cfg->envs_per_block : 4;
-    h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs};
+    h->ws.assign((size_t)cfg->n_envs * FM_WS_FLOATS, 0.f);
+    h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, h->ws.data()};
     *out = h; return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

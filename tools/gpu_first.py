@@ -6,7 +6,7 @@ import __graft_entry__ as g
 g.smoke()
 from factory_marl_b200.vec_env import FactoryVecEnv
 res = []
-for (n, E, outer, inner) in [(4096, 4, 0, 0), (4096, 2, 0, 0), (4096, 1, 0, 0), (16384, 1, 0, 0), (16384, 2, 0, 0), (8192, 1, 0, 0)]:
+for (n, E, outer, inner) in [(4096, 4, 0, 0), (4096, 1, 0, 0), (16384, 1, 0, 0), (16384, 4, 0, 0)]:
     env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=n, num_arms=2, seeds=list(range(42, 42 + n)), envs_per_block=E,
                         pgs_outer=outer, pgs_inner=inner, gripper_to_closest_cube_reward_factor=0.2,
                         closest_cube_to_bucket_reward_factor=0.4, base_reward=0.4)
