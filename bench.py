@@ -239,7 +239,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{n} batched TaskEnv per GPU ({ENV_CLASS} action map), two arms, fixed random policy (178-128-128-16 tanh MLP, seed 0), 100 sub-steps per step",
                            "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB write)", "preroll_steps": args.preroll,
-                           "solver": "PGS, adaptive (<= 8 sweeps, tol 1e-3 m/s^2), forces persisted across sub-steps; resting hidden cubes asleep"},
+                           "solver": "PGS, adaptive (<= 4 sweeps, tol 1e-3 m/s^2), forces persisted across sub-steps; resting hidden cubes asleep"},
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": DRAM_BYTES_PER_ENV_NCU * n,
                              "peak_source": peak_kind, "kernel": "fm_step_kernel", "kernel_ms": kern_ms, "bytes_per_env_step": bytes_per_env,
                              "note": "the step kernel is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); see roofline_fp32"},

@@ -127,13 +127,16 @@ struct EnvS {
 #define FM_FLAG_QUEUE_OVERFLOW 4
 #define FM_FLAG_NAN 8
 
-// side descriptor packing: type (2 bits) | idx (6 bits: cube k or arm*16+body) | slot (4 bits) per side; bit 31 = arm geom involved
+// side descriptor packing: type (2 bits) | idx (7 bits: cube k or arm*16+body) | slot (6 bits) per side = 15 bits; two sides per
+// contact word, bit 30 = an arm geom is involved
 FM_HD int pack_side(int type, int idx, int slot) { return type | (idx << 2) | (slot << 9); }
 FM_HD int side_type(int s) { return s & 3; }
 FM_HD int side_idx(int s) { return (s >> 2) & 127; }
-FM_HD int side_slot(int s) { return (s >> 9) & 15; }
+FM_HD int side_slot(int s) { return (s >> 9) & 63; }
+#define FM_SIDE_BITS 15
+#define FM_SIDE_MASK 32767
 FM_HD int contact_node(int cs, int q) {   // island node of side q of a packed contact: cube k -> k, arm a -> 10 + a, else -1
-  int sd = (cs >> (13 * q)) & 8191;
+  int sd = (cs >> (FM_SIDE_BITS * q)) & FM_SIDE_MASK;
   int ty = side_type(sd), ix = side_idx(sd);
   return ty == FM_SIDE_CUBE ? ix : (ty == FM_SIDE_ARM ? FM_NCUBE + (ix >> 4) : -1);
 }
@@ -488,7 +491,7 @@ FM_HD void emit(EnvS<NA>& s, int g1, int g2, int side1, int side2, bool armgeom,
     int i = slot + k;
     if (i >= FM_MAXCON) { FM_ATOMIC_OR(&s.flags, FM_FLAG_CON_OVERFLOW); break; }
     s.raw_key[i] = (g1 << 13) | (g2 << 4) | k;
-    s.raw_g[i] = side1 | (side2 << 13) | (armgeom ? (1 << 30) : 0);
+    s.raw_g[i] = side1 | (side2 << FM_SIDE_BITS) | (armgeom ? (1 << 30) : 0);
     s.raw_d[i][0] = rc[k].pos.x; s.raw_d[i][1] = rc[k].pos.y; s.raw_d[i][2] = rc[k].pos.z;
     s.raw_d[i][3] = rc[k].n.x; s.raw_d[i][4] = rc[k].n.y; s.raw_d[i][5] = rc[k].n.z; s.raw_d[i][6] = rc[k].dist;
   }
@@ -680,13 +683,13 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
       if (s.raw_key[k] < key) {
         rank++;
         int g = s.raw_g[k];
-        slot_base += (side_type(g & 8191) == FM_SIDE_ARM ? 1 : 0) + (side_type((g >> 13) & 8191) == FM_SIDE_ARM ? 1 : 0);
+        slot_base += (side_type(g & FM_SIDE_MASK) == FM_SIDE_ARM ? 1 : 0) + (side_type((g >> FM_SIDE_BITS) & FM_SIDE_MASK) == FM_SIDE_ARM ? 1 : 0);
       }
     }
     int c = rank;
     int g1 = key >> 13, g2 = (key >> 4) & 511;
     int rg = s.raw_g[ri];
-    int sd1 = rg & 8191, sd2 = (rg >> 13) & 8191; bool armgeom = (rg >> 30) & 1;
+    int sd1 = rg & FM_SIDE_MASK, sd2 = (rg >> FM_SIDE_BITS) & FM_SIDE_MASK; bool armgeom = (rg >> 30) & 1;
     f3 p = mk3(s.raw_d[ri][0], s.raw_d[ri][1], s.raw_d[ri][2]), n = mk3(s.raw_d[ri][3], s.raw_d[ri][4], s.raw_d[ri][5]);
     float dist = s.raw_d[ri][6];
     f3 t1, t2; make_frame3(n, t1, t2);
@@ -719,7 +722,7 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
           for (int i = 0; i < 9; ++i) { float acc = 0.f; for (int k = 0; k < 9; ++k) acc += s.Minv[a][9 * i + k] * J[9 * q + k]; Bv[9 * q + i] = acc; }
       }
     }
-    s.c_side[c] = sds[0] | (sds[1] << 13) | (armgeom ? (1 << 30) : 0);
+    s.c_side[c] = sds[0] | (sds[1] << FM_SIDE_BITS) | (armgeom ? (1 << 30) : 0);
     {
       int cs2 = s.c_side[c];
       int n0 = contact_node(cs2, 0), n1 = contact_node(cs2, 1);
@@ -908,8 +911,8 @@ FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool first, f
   int cs = s.c_side[c];
   f3 p = ld3(s.c_p[c]), n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); f3 t2 = cross3(n, t1);
   SideW A, B;
-  side_prepare(s, m, cs & 8191, -1.f, p, n, t1, t2, A);
-  side_prepare(s, m, (cs >> 13) & 8191, +1.f, p, n, t1, t2, B);
+  side_prepare(s, m, cs & FM_SIDE_MASK, -1.f, p, n, t1, t2, A);
+  side_prepare(s, m, (cs >> FM_SIDE_BITS) & FM_SIDE_MASK, +1.f, p, n, t1, t2, B);
   float mu = s.c_mu[c], R = s.c_R[c];
   const float* W = s.c_W[c];
   float f[4] = {s.c_f[c][0], s.c_f[c][1], s.c_f[c][2], s.c_f[c][3]};
@@ -991,7 +994,10 @@ FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
     for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) arm_rows_visit(s, a, true);
     for (int ci = c0; ci < c1; ++ci) contact_visit(s, m, s.isl_list[ci], true, belt_sum);
     FM_DBG(fm_dbg_islands++;)
-    for (int it = 0; it < inner; ++it) {
+    // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
+    // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236)
+    const int cap = (has_arm && c1 > c0) ? 8 * inner : inner;
+    for (int it = 0; it < cap; ++it) {
       float maxd = 0.f; belt_sum = 0.f;
       FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0;)
       for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, false));

@@ -10,7 +10,7 @@
 #define FM_NABOX 9          // gripper boxes per arm (gripper.xml:6-41)
 #define FM_MAX_SBOX 12      // table + 2 x (bucket floor + 4 fences)
 #define FM_MAXCON 56        // contacts per env
-#define FM_MAXARMSIDE 10    // contact sides that touch an arm (each stores 3x9 Jacobian + 3x9 Minv J^T)
+#define FM_MAXARMSIDE 40    // contact sides that touch an arm (a grasped cube alone makes 16+); stored in global scratch (each stores 3x9 Jacobian + 3x9 Minv J^T)
 #define FM_MAX_ARMS 4
 #define FM_NCLASS 4
 

@@ -120,3 +120,34 @@ def test_auto_reset_and_episode_info():
             done_seen = True
             break
     assert done_seen
+
+
+def test_mean_collected_objects_within_oracle_ci():
+    """BASELINE.json: mean collected objects under a fixed policy must fall within the reference's 95% confidence interval.
+    Fixed policy = IK base policy, 2 arms; interval from 96 oracle episodes (tests/golden/ik_policy_stats.json, made by
+    tools/make_policy_stats.py — the reference itself cannot run here); GPU: 1024 envs, same horizon and bookkeeping."""
+    import json, os
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    from tests.parity_util import GOLDEN
+    st = json.load(open(os.path.join(GOLDEN, "ik_policy_stats.json")))
+    N, H = 1024, st["horizon"]
+    env = FactoryVecEnv("FactoryManipulationEnv", num_envs=N, num_arms=2, seeds=list(range(42, 42 + N)), auto_reset=True)
+    env.reset()
+    done = torch.zeros(N, dtype=torch.bool, device="cuda")
+    total = torch.zeros(N, device="cuda"); length = torch.full((N,), float(H), device="cuda")
+    dummy = torch.zeros((N, 1), device="cuda")
+    for t in range(H):
+        obs, rew, term, _ = env.step(dummy)
+        first = term & ~done
+        ep = env.core.ep_info
+        total = torch.where(first, ep[:, 2] + ep[:, 3], total)
+        length = torch.where(first, torch.full_like(length, t + 1.0), length)
+        done |= term
+    sc = env.core.scores.float().sum(dim=1)
+    total = torch.where(done, total, sc)
+    mean_total, mean_len = float(total.mean()), float(length.mean())
+    lo, hi = st["ci95_total"]
+    print("GPU mean total %.3f (oracle %.3f, CI [%.3f, %.3f]); mean length %.1f (oracle %.1f, CI %s)" %
+          (mean_total, st["mean_total"], lo, hi, mean_len, st["mean_length"], st["ci95_length"]))
+    assert lo <= mean_total <= hi, (mean_total, lo, hi)
+    assert st["ci95_length"][0] <= mean_len <= st["ci95_length"][1], (mean_len, st["ci95_length"])
