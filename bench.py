@@ -142,7 +142,7 @@ def run_ours(args):
     n = args.envs
     K, W = args.steps, max(args.warmup, 3)
     env = FactoryVecEnv(ENV_CLASS, num_envs=n, num_arms=2, seeds=list(range(42 + rank * n, 42 + (rank + 1) * n)),
-                        device=dev, **ENV_KW)
+                        device=dev, envs_per_block=args.envs_per_block, **ENV_KW)
     # fixed random policy: freshly initialised 178->128->128->16 tanh MLP, orthogonal init, torch seed 0, log_std = 0
     pol = fppo.PolicyValueNet(env.core.obs_dim, env.core.act_dim, discrete=False, device=dev, seed=0)
     obs = env.reset()
@@ -187,7 +187,8 @@ def run_ours(args):
 
     # ---- e2e: through the public VecEnv API with HOST buffers (pinned), H2D actions + D2H obs/reward/done every step
     host_act = torch.empty((n, 16), dtype=torch.float32).pin_memory()
-    host_act.copy_(torch.from_numpy(np.random.default_rng(rank).uniform(-1, 1, (n, 16)).astype(np.float32)))
+    # same action statistics as the fixed random policy of the device-resident arm (N(~0, 1) clipped to [-1, 1])
+    host_act.copy_(torch.from_numpy(np.clip(np.random.default_rng(rank).normal(0, 1, (n, 16)), -1, 1).astype(np.float32)))
     host_obs = torch.empty((n, env.core.obs_dim), dtype=torch.float32).pin_memory()
     host_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
     host_done = torch.empty((n,), dtype=torch.bool).pin_memory()
@@ -270,6 +271,7 @@ def main():
     ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--ppo-steps", type=int, default=8)
     ap.add_argument("--preroll", type=int, default=60)
+    ap.add_argument("--envs-per-block", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
