@@ -16,6 +16,12 @@ static thread_local std::string g_ppo_err;
 extern "C" const char* fm_ppo_last_error(void) { return g_ppo_err.c_str(); }
 
 typedef __nv_bfloat16 bf16;
+extern "C" int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const void* w1, const void* w2, const void* w3,
+                                  const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
+                                  int* status, void* stream);
+extern "C" const char* fm_tc5_last_error(void);
+static int g_use_tc5 = 1;     // rollout forward on the tcgen05 path (fm_mlp_tc5.cu); 0 = the mma.sync GEMM chain
+extern "C" void fm_ppo_use_tcgen05(int on) { g_use_tc5 = on; }
 
 // ----------------------------------------------------------------------------------------------------------------------
 // Generic small GEMM on the tensor cores: C[M,N] = epi(A[M,K] * B[K,N]); bf16 operands, fp32 accumulate.
@@ -376,10 +382,23 @@ int fm_policy_forward(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* o
                       void* act_env, float* act_raw, float* logp, float* value, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n > ws->cap || n % 64) { g_ppo_err = "fm_policy_forward: n must be a multiple of 64 and <= workspace capacity"; return 1; }
-  size_t tot = (size_t)n * net->obs_pad;
-  cast_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(obs, n, net->obs_dim, ws->x, net->obs_pad, nullptr);
-  if (int rc = mlp_forward(net, ws, 0, n, s)) return rc;
-  if (value) { if (int rc = mlp_forward(net, ws, 1, n, s)) return rc; copy_col0_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws->out[1], 16, n, value); }
+  if (g_use_tc5) {
+    // fused tcgen05 path: the three layers of a net in one kernel, hidden activations stay in shared memory / TMEM
+    const bf16* P = net->params_bf16; const float* Pf = net->params;
+    int* status = reinterpret_cast<int*>(ws->scal + 8);
+    if (int rc = fm_mlp_forward_tc5(obs, net->obs_dim, net->obs_dim, nullptr, P + net->w1[0], P + net->w2[0], P + net->w3[0], Pf + net->b1[0],
+                                    Pf + net->b2[0], Pf + net->b3[0], ws->out[0], net->out_pad, nullptr, nullptr, n, net->obs_pad, status, stream)) { g_ppo_err = fm_tc5_last_error(); return rc; }
+    if (value) {
+      if (int rc = fm_mlp_forward_tc5(obs, net->obs_dim, net->obs_dim, nullptr, P + net->w1[1], P + net->w2[1], P + net->w3[1], Pf + net->b1[1],
+                                      Pf + net->b2[1], Pf + net->b3[1], ws->out[1], 16, nullptr, nullptr, n, net->obs_pad, status, stream)) { g_ppo_err = fm_tc5_last_error(); return rc; }
+      copy_col0_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws->out[1], 16, n, value);
+    }
+  } else {
+    size_t tot = (size_t)n * net->obs_pad;
+    cast_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(obs, n, net->obs_dim, ws->x, net->obs_pad, nullptr);
+    if (int rc = mlp_forward(net, ws, 0, n, s)) return rc;
+    if (value) { if (int rc = mlp_forward(net, ws, 1, n, s)) return rc; copy_col0_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws->out[1], 16, n, value); }
+  }
   if (net->discrete) sample_categorical_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws->out[0], net->out_pad, n, net->act_dim, seed, (int*)act_env, act_raw, logp, deterministic);
   else sample_gaussian_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws->out[0], net->out_pad, net->params + net->log_std, n, net->act_dim, seed, act_raw, (float*)act_env, logp, deterministic);
   PPO_CUDA(cudaGetLastError());

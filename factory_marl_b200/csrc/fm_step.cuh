@@ -540,6 +540,14 @@ FM_HD void narrow_arm_geom_vs(EnvS<NA>& s, const FmDevModel& m, int a2, int b2, 
   f3 sq = mk3(0, 0, 0); float sr = 0.f; int sg = 0; GeomBox g2;
   if (is_sph) { int si = s0 + j; sq = p2 + rmul(R2, ld3(m.sph_pos[si])); sr = m.sph_r[si]; sg = m.arm_first_geom[a2] + m.sph_geom[si]; }
   else get_box(s, m, FM_CL_ARM, a2 * FM_NARMBODY + b2, x0 + (j - ns), g2, RidB);
+  if (k1 == FM_CL_ARM || k1 == FM_CL_CUBE) {
+    // mid phase: this one geom against the first cluster's bounding sphere (conservative; most near cluster pairs of
+    // neighbouring links have no near geom pair at all)
+    const float* bb = s.bnd[k1 == FM_CL_CUBE ? i1 : FM_NCUBE + i1];
+    f3 gc = is_sph ? sq : g2.p; float gr = is_sph ? sr : norm3(g2.hs);
+    f3 dd = gc - mk3(bb[0], bb[1], bb[2]); float rr = gr + bb[3];
+    if (dot3(dd, dd) > rr * rr) return;
+  }
   if (k1 == FM_CL_PLANE) {
     if (is_sph) { int n = col_plane_sphere(sq, sr, rc); emit(s, 0, sg, pack_side(FM_SIDE_STATIC, 0, 0), side2, true, rc, n); }
     else { int n = col_plane_box(g2.p, g2.R, g2.hs, rc); emit(s, 0, g2.geom, pack_side(FM_SIDE_STATIC, 0, 0), g2.side, true, rc, n); }

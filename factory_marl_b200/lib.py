@@ -18,6 +18,7 @@ _DEPS = {
     "fm_lib.cu": ["fm_lib.cu", "fm_types.h", "fm_math.cuh", "fm_collide.cuh", "fm_step.cuh", "fm_task.cuh", "fm_driver.cuh", "fm_ik.cuh",
                   "fm_host_model.h", "fm_host_common.h", "../../include/fm_api.h", "../../include/fm_blob.h"],
     "fm_ppo.cu": ["fm_ppo.cu", "../../include/fm_api.h"],
+    "fm_mlp_tc5.cu": ["fm_mlp_tc5.cu"],
 }
 
 

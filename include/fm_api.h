@@ -99,6 +99,11 @@ int fm_ppo_update(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, 
 int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, int step,
                  float* stats, void* stream);
 int fm_ppo_sync_bf16(const fm_ppo_net* net, void* stream);
+/* fused 3-layer MLP forward of one net on tcgen05 (TMEM accumulators); used by fm_policy_forward unless switched off */
+int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const void* w1, const void* w2, const void* w3,
+                       const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
+                       int* status, void* stream);
+void fm_ppo_use_tcgen05(int on);
 const char* fm_ppo_last_error(void);
 
 #ifdef __cplusplus

@@ -156,3 +156,26 @@ def test_ppo_learn_smoke_and_sb3_roundtrip(tmp_path):
     other.set_sb3_state_dict({k: v.cuda() for k, v in sd.items()})
     for k, v in other.sb3_state_dict().items():
         assert torch.equal(v, sd[k])
+
+
+@pytest.mark.parametrize("obs_dim,act_dim,discrete", [(178, 16, False), (258, 4, True), (226, 32, False)])
+def test_tcgen05_mlp_matches_mma_sync_and_fp32(obs_dim, act_dim, discrete):
+    """The fused tcgen05 forward (TMEM accumulators) against the mma.sync GEMM chain and a fp32 torch MLP."""
+    from factory_marl_b200.ppo import PolicyValueNet
+    pol = PolicyValueNet(obs_dim, act_dim, discrete, seed=11, capacity=640)
+    sd, fwd = _torch_nets(pol)
+    x = torch.randn(640, obs_dim, device="cuda") * 1.5
+    pol.lib.fm_ppo_use_tcgen05(1)
+    pol.forward(x, deterministic=True)
+    out_tc5 = pol._bufs["out"][0][:640].clone(); val_tc5 = pol.value[:640].clone()
+    status = int(pol._bufs["scal"][8:9].view(torch.int32)[0])
+    pol.lib.fm_ppo_use_tcgen05(0)
+    pol.forward(x, deterministic=True)
+    out_mma = pol._bufs["out"][0][:640].clone(); val_mma = pol.value[:640].clone()
+    pol.lib.fm_ppo_use_tcgen05(1)
+    pi, v = fwd(x)
+    n_out = pi.shape[1]
+    assert status == 0, "mbarrier wait timed out in the tcgen05 kernel"
+    assert torch.allclose(out_tc5[:, :n_out], pi, atol=2e-2, rtol=2e-2), float((out_tc5[:, :n_out] - pi).abs().max())
+    assert torch.allclose(val_tc5, v, atol=2e-2, rtol=2e-2)
+    assert torch.allclose(out_tc5, out_mma, atol=1e-2, rtol=1e-2) and torch.allclose(val_tc5, val_mma, atol=1e-2, rtol=1e-2)
