@@ -186,20 +186,22 @@ def run_ours(args):
     value = world * n * K / (total_ms * 1e-3)
 
     # ---- e2e: through the public VecEnv API with HOST buffers (pinned), H2D actions + D2H obs/reward/done every step
-    host_act = torch.empty((n, 16), dtype=torch.float32).pin_memory()
-    # same action statistics as the fixed random policy of the device-resident arm (N(~0, 1) clipped to [-1, 1])
-    host_act.copy_(torch.from_numpy(np.clip(np.random.default_rng(rank).normal(0, 1, (n, 16)), -1, 1).astype(np.float32)))
+    Ke = max(3, min(K, 10))
+    # same action statistics as the fixed random policy of the device-resident arm: a fresh N(~0, 1) draw clipped to [-1, 1]
+    # every control step (the host-side user computes its actions before the call; the draw itself is not timed)
+    rng_e = np.random.default_rng(rank)
+    host_acts = [torch.from_numpy(np.clip(rng_e.normal(0, 1, (n, 16)), -1, 1).astype(np.float32)).pin_memory() for _ in range(Ke)]
+    host_act = host_acts[0]
     host_obs = torch.empty((n, env.core.obs_dim), dtype=torch.float32).pin_memory()
     host_rew = torch.empty((n,), dtype=torch.float32).pin_memory()
     host_done = torch.empty((n,), dtype=torch.bool).pin_memory()
-    Ke = max(3, min(K, 10))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(Ke):
-        a_dev = host_act.to(dev, non_blocking=True)
+        a_dev = host_acts[k].to(dev, non_blocking=True)
         o2, rew, term, _ = env.step(a_dev)
         host_obs.copy_(o2, non_blocking=True); host_rew.copy_(rew, non_blocking=True); host_done.copy_(term, non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the user reads the result on the host every step

@@ -88,10 +88,11 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
   }
 }
 
-template <int NA, int E, class Run>
+// TW = warps per block (default: one warp per env of the block)
+template <int NA, int E, int TW = E, class Run>
 FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class,
                          const FmEnvCfg& cfg, const FmStatePtrs& st, const FmStepArgs& ar, int env0) {
-  const int T = 32 * E;
+  const int T = 32 * TW;
   typedef Lay<NA> L;
   const int obs_dim = L::obs_dim(cfg.env_class);
   run([&](int tid) { ph_load<NA, E>(S, TS, st, env0, tid, T); });
@@ -126,10 +127,11 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
     run([&](int tid) { ph_island_lists<NA, E>(S, tid, T); ph_smooth<NA, E>(S, m, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 1); });
+    run([&](int tid) { ph_check<NA, E>(S, m, tid, T); });
     run([&](int tid) { ph_pgs<NA, E>(S, m, tid, T, cfg.pgs_inner, cfg.pgs_tol); });
-    run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); });
+    // belt lane: contact term of the belt dof (same lane as the belt row of ph_integrate), then integration
+    run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 2); });
-    run([&](int tid) { if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });
   }
   if (ar.mode == 2) {   // debug: store the raw state, pre-edit == current
     run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, tid, T); for (int w = tid; w < E; w += T) TS[w].done_prev = 0; });

@@ -1,0 +1,58 @@
+// fm_kernel.cuh — the fused env-step kernel and its launcher, one explicit instantiation per block shape (fm_step_shape_*.cu).
+//   NA = arms, E = envs per block (state of E envs lives in shared memory for the 100 sub-steps), TW = warps per block.
+// Work items of a phase are spread over all 32*TW lanes of the block (item w -> env w % E); phases are separated by
+// __syncthreads().  fm_lib.cu only sees the declaration of fm_launch_step and the extern template lines below.
+#pragma once
+#include <cuda_runtime.h>
+#include "fm_driver.cuh"
+
+struct FmLaunch { const FmDevModel* model; const unsigned int* cpairs; const int* geom_class; FmEnvCfg cfg; FmStatePtrs st; };
+
+template <int NA, int E, int TW>
+cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t s);
+
+#ifdef FM_KERNEL_IMPL
+
+struct DevRun {
+  template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); __syncthreads(); }
+};
+
+template <int NA, int E, int TW>
+__global__ void __launch_bounds__(32 * TW, 1) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned int* __restrict__ cpairs,
+                                                             const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EnvS<NA>* S = reinterpret_cast<EnvS<NA>*>(smem_raw);
+  TaskS* TS = reinterpret_cast<TaskS*>(S + E);
+  // zero the block's shared state (counters, lists)
+  {
+    int* z = reinterpret_cast<int*>(smem_raw);
+    const int nw = (int)((E * (sizeof(EnvS<NA>) + sizeof(TaskS))) / 4);
+    for (int i = threadIdx.x; i < nw; i += 32 * TW) z[i] = 0;
+    __syncthreads();
+  }
+  __builtin_assume(__isShared(S)); __builtin_assume(__isShared(TS));
+  DevRun run;
+  fm_block_step<NA, E, TW>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
+}
+
+template <int NA, int E, int TW>
+cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t s) {
+  const size_t smem = E * (sizeof(EnvS<NA>) + sizeof(TaskS));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fm_step_kernel<NA, E, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int nblk = (L.st.n + E - 1) / E;
+  fm_step_kernel<NA, E, TW><<<nblk, 32 * TW, smem, s>>>(L.model, L.cpairs, L.geom_class, L.cfg, L.st, ar);
+  return cudaGetLastError();
+}
+#else
+extern template cudaError_t fm_launch_step<2, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<2, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<2, 14, 12>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<4, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<4, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<4, 7, 7>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+#endif

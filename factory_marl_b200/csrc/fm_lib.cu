@@ -1,6 +1,7 @@
 // fm_lib.cu — CUDA kernels (sm_100a) + the C-ABI of include/fm_api.h.
 // Kernels:
-//   fm_step_kernel<NA,E>   fused env step: 100 x mj_step-equivalent + task logic for E envs per CTA (fm_driver.cuh)
+//   fm_step_kernel<NA,E,TW> fused env step: 100 x mj_step-equivalent + task logic for E envs per CTA (fm_kernel.cuh,
+//                          instantiated per block shape in fm_step_shape_*.cu)
 //   fm_ik_kernel<NA>       IK base policy + FSM, fp64, thread per env (fm_ik.cuh)
 // No CPU fallback: every entry point launches CUDA work or fails with an error.
 #include <cuda_runtime.h>
@@ -8,34 +9,10 @@
 #include <new>
 #include "fm_host_common.h"
 #include "fm_ik.cuh"
-
-#ifndef FM_DEFAULT_E
-#define FM_DEFAULT_E 4
-#endif
+#include "fm_driver.cuh"
+#include "fm_kernel.cuh"
 static thread_local std::string g_err;
 #define FM_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return 2; } } while (0)
-
-struct DevRun {
-  template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); __syncthreads(); }
-};
-
-template <int NA, int E>
-__global__ void __launch_bounds__(32 * E) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned int* __restrict__ cpairs,
-                                                         const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  EnvS<NA>* S = reinterpret_cast<EnvS<NA>*>(smem_raw);
-  TaskS* TS = reinterpret_cast<TaskS*>(S + E);
-  // zero the block's shared state (counters, lists)
-  {
-    int* z = reinterpret_cast<int*>(smem_raw);
-    const int nw = (int)((E * (sizeof(EnvS<NA>) + sizeof(TaskS))) / 4);
-    for (int i = threadIdx.x; i < nw; i += 32 * E) z[i] = 0;
-    __syncthreads();
-  }
-  __builtin_assume(__isShared(S)); __builtin_assume(__isShared(TS));
-  DevRun run;
-  fm_block_step<NA, E>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
-}
 
 template <int NA>
 __global__ void fm_ik_kernel(const FmIkModel* __restrict__ ik, FmEnvCfg cfg, FmStatePtrs st, float* obs, int obs_dim) {
@@ -52,25 +29,19 @@ struct fm_handle {
   long long launches = 0;
 };
 
-template <int NA, int E>
-static int launch_step(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
-  size_t smem = E * (sizeof(EnvS<NA>) + sizeof(TaskS));
-  static bool attr_set = false;
-  if (!attr_set) { FM_CUDA(cudaFuncSetAttribute(fm_step_kernel<NA, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-  int nblk = (h->cfg.n_envs + E - 1) / E;
-  fm_step_kernel<NA, E><<<nblk, 32 * E, smem, s>>>(h->d_model, h->d_cpairs, h->d_geom_class, h->cfg, h->st, ar);
-  FM_CUDA(cudaGetLastError());
-  h->launches++;
-  return 0;
-}
+// Block shapes built into the library (one translation unit each, fm_step_shape_*.cu): NA arms, E envs per block, TW warps.
+//   E = 14 / TW = 12 (two arms) and E = 7 / TW = 7 (four arms): one block per SM, all warps on the same stretch of code (the
+//   hot loop is ~120 KB of SASS against a 32 KB L1.5 instruction cache; independent single-warp blocks thrash it), 4096
+//   envs = 2 (4) full waves of 148 blocks.  E = 4 and E = 1: small batches, tests.
 static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
-  if (h->hm.n_arms == 2) {
-    if (h->E == 1) return launch_step<2, 1>(h, ar, s);
-    return launch_step<2, 4>(h, ar, s);
-  }
-  if (h->E == 1) return launch_step<4, 1>(h, ar, s);
-  return launch_step<4, 4>(h, ar, s);
+  FmLaunch L{h->d_model, h->d_cpairs, h->d_geom_class, h->cfg, h->st};
+  cudaError_t e;
+  if (h->hm.n_arms == 2) e = h->E == 14 ? fm_launch_step<2, 14, 12>(L, ar, s) : (h->E == 1 ? fm_launch_step<2, 1, 1>(L, ar, s) : fm_launch_step<2, 4, 4>(L, ar, s));
+  else e = h->E == 7 ? fm_launch_step<4, 7, 7>(L, ar, s) : (h->E == 1 ? fm_launch_step<4, 1, 1>(L, ar, s) : fm_launch_step<4, 4, 4>(L, ar, s));
+  if (e != cudaSuccess) { g_err = std::string("fm_step_kernel launch: ") + cudaGetErrorString(e); return 2; }
+  h->launches++;
+  return 0;
 }
 
 extern "C" {
@@ -86,8 +57,10 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4 are built");
     if (cfg->env_class < 0 || cfg->env_class > 6) throw std::runtime_error("bad env_class");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
+    // envs per block: 1 | 4 | the one-block-per-SM shape (14 with two arms, 7 with four); 0 = by batch size
+    const int big = h->hm.n_arms == 2 ? 14 : 7;
     int E = cfg->envs_per_block;
-    h->E = (E == 1 || E == 4) ? E : FM_DEFAULT_E;
+    h->E = (E == 1 || E == 4 || E == big) ? E : (cfg->n_envs >= 148 * big ? big : 4);
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, nullptr};
     FM_CUDA(cudaMalloc(&h->d_model, sizeof(FmDevModel)));
     FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));
@@ -98,8 +71,9 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     FM_CUDA(cudaMalloc(&h->d_geom_class, h->hm.geom_class.size() * sizeof(int)));
     FM_CUDA(cudaMemcpy(h->d_geom_class, h->hm.geom_class.data(), h->hm.geom_class.size() * sizeof(int), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_dump, sizeof(FmDebugDump)));
-    FM_CUDA(cudaMalloc(&h->d_ws, (size_t)cfg->n_envs * FM_WS_FLOATS * sizeof(float)));
-    FM_CUDA(cudaMemset(h->d_ws, 0, (size_t)cfg->n_envs * FM_WS_FLOATS * sizeof(float)));
+    const size_t ws_rows = (size_t)cfg->n_envs + 32;   // + padding slots of the last block
+    FM_CUDA(cudaMalloc(&h->d_ws, ws_rows * FM_WS_FLOATS * sizeof(float)));
+    FM_CUDA(cudaMemset(h->d_ws, 0, ws_rows * FM_WS_FLOATS * sizeof(float)));
     h->st.ws = h->d_ws;
     *out = h;
     return 0;

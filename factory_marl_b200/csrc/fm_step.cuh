@@ -35,6 +35,7 @@ static inline int fm_host_max(int* p, int v) { int o = *p; *p = o > v ? o : v; r
 
 #if !defined(__CUDACC__)
 static long long fm_dbg_sweeps = 0, fm_dbg_visits = 0, fm_dbg_islands = 0;   // host logic-test build only
+static long long fm_dbg_cnt[32] = {0};
 #define FM_DBG(x) x
 #else
 #define FM_DBG(x)
@@ -58,6 +59,9 @@ static long long fm_dbg_sweeps = 0, fm_dbg_visits = 0, fm_dbg_islands = 0;   // 
 // packed lower-triangular index
 FM_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+#ifndef FM_ENVS_PAD
+#define FM_ENVS_PAD 5
+#endif
 template <int NA>
 struct EnvS {
   static const int NV = 61 + 9 * NA, NQ = 71 + 9 * NA, NU = 1 + 8 * NA, NNODE = FM_NCUBE + NA;
@@ -77,7 +81,6 @@ struct EnvS {
   // ---- acceleration stage
   float acc[NV];
   float belt_acc_smooth, belt_S;
-  float belt_part[NNODE];                   // per-island belt force partial sums (summed in fixed order: run-to-run determinism)
   // ---- arm-local rows (joint equality gripper.xml:46-49, joint limits)
   int arow_n[NA], arow_code[NA][FM_AROW];   // code: dof | sign<<8 (sign bit 1 = negative) ; 0x1000 = equality
   float arow_aref[NA][FM_AROW], arow_R[NA][FM_AROW], arow_f[NA][FM_AROW];
@@ -118,7 +121,7 @@ struct EnvS {
   int prev_arow_n[NA], prev_arow_code[NA][FM_AROW];
   float prev_arow_f[NA][FM_AROW];
   int c_key[FM_MAXCON];
-  int pad_;
+  int pad_[FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 4 (mod 32): envs of one block start on different shared-memory banks
 };
 
 // flags
@@ -517,9 +520,10 @@ FM_HD void pair_box_box(EnvS<NA>& s, const GeomBox& x, const GeomBox& y, bool ar
   if (g1.axis_aligned && !g2.axis_aligned) {      // small box on the top face of a big axis-aligned box (belt, table): fast path.
     RawC rf[4];                                   // Only with the big box as geom1: on exact face-axis ties the general routine
     int nf = col_box_on_face(g1.p, g1.hs, g2.p, g2.R, g2.hs, true, rf);   // prefers box 1's face, which must be the big one.
-    if (nf >= 0) { emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rf, nf); return; }
+    if (nf >= 0) { FM_DBG(fm_dbg_cnt[27]++;) emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rf, nf); return; }
   }
-  if (far_sphere_box(g2.p, norm3(g2.hs), g1.p, g1.R, g1.hs) || far_sphere_box(g1.p, norm3(g1.hs), g2.p, g2.R, g2.hs)) return;
+  if (far_sphere_box(g2.p, norm3(g2.hs), g1.p, g1.R, g1.hs) || far_sphere_box(g1.p, norm3(g1.hs), g2.p, g2.R, g2.hs)) { FM_DBG(fm_dbg_cnt[28]++;) return; }
+  FM_DBG(fm_dbg_cnt[29]++; fm_dbg_cnt[30] += armgeom;)
   RawC rc[8];
   int n = col_box_box(g1.p, g1.R, g1.hs, g2.p, g2.R, g2.hs, rc);
   emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rc, n);
@@ -842,6 +846,7 @@ FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
     EnvS<NA>& s = S[w];
     int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
     s.ncon = nraw;
+    FM_DBG(fm_dbg_cnt[0]++; fm_dbg_cnt[1] += nraw; fm_dbg_cnt[2] += s.nqueue; fm_dbg_cnt[3] += s.need_union; for (int k = 0; k < FM_NCUBE; ++k) fm_dbg_cnt[26] += !s.cube_sleep[k];)
     if (!s.need_union) continue;
     int* root = s.isl_root;
     for (int c = 0; c < nraw; ++c) {
@@ -880,20 +885,40 @@ FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
   }
 }
 
-// phase: actuation + smooth acceleration (mj_fwdActuation, mj_fwdAcceleration)
+// phase: actuation + smooth acceleration (mj_fwdActuation, mj_fwdAcceleration), plus the warm start of the constraint solve:
+// every lane owns one cube (6 rows of acc) or one arm dof and adds Minv J^T f of the previous solve's forces for the contacts /
+// arm rows that touch it, in ascending contact order (fixed order: run-to-run determinism).
 template <int NA, int E>
 FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int per = 1 + FM_NCUBE + 9 * NA;
   for (int w = tid; w < per * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
+    const int ncon = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
     if (i == 0) {
       float c = clampf(s.ctrl_target[0], m.ctrl_lo[0], m.ctrl_hi[0]);
       float f = m.belt_kv * (c - s.belt_v) - m.belt_damp * s.belt_v;
       s.belt_acc_smooth = f / m.belt_mass; s.acc[0] = s.belt_acc_smooth + s.belt_S;
     } else if (i <= FM_NCUBE) {
-      float* a = &s.acc[1 + 6 * (i - 1)];
-      a[0] = 0; a[1] = 0; a[2] = -m.g; a[3] = 0; a[4] = 0; a[5] = 0;
+      int k = i - 1;
+      float a[6] = {0, 0, -m.g, 0, 0, 0};
+      if (!s.cube_sleep[k]) {
+        f3 xk = ld3(s.cube_x[k]); float invm = m.cube_invm[k], invI = m.cube_invI[k];
+        for (int c = 0; c < ncon; ++c) {
+          int cs = s.c_side[c];
+          int sd0 = cs & FM_SIDE_MASK, sd1 = (cs >> FM_SIDE_BITS) & FM_SIDE_MASK;
+          bool h0 = side_type(sd0) == FM_SIDE_CUBE && side_idx(sd0) == k, h1 = side_type(sd1) == FM_SIDE_CUBE && side_idx(sd1) == k;
+          if (!h0 && !h1) continue;
+          f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); f3 t2 = cross3(n, t1);
+          const float* f = s.c_f[c]; float mu = s.c_mu[c];
+          float l0 = f[0] + f[1] + f[2] + f[3], l1 = mu * (f[0] - f[1]), l2 = mu * (f[2] - f[3]);
+          f3 F = (n * l0 + t1 * l1 + t2 * l2) * (h0 ? -1.f : 1.f);
+          f3 fl = F * invm, fa = cross3(ld3(s.c_p[c]) - xk, F) * invI;
+          a[0] += fl.x; a[1] += fl.y; a[2] += fl.z; a[3] += fa.x; a[4] += fa.y; a[5] += fa.z;
+        }
+      }
+      float* o = &s.acc[1 + 6 * k];
+      for (int q = 0; q < 6; ++q) o[q] = a[q];
     } else {
       int ad = i - 1 - FM_NCUBE; int a = ad / 9, r = ad % 9;
       // row r of Minv * (tau - bias)
@@ -907,15 +932,41 @@ FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       float f = clampf(m.g_kp * c - m.g_kb * len - m.g_kd * lv, m.g_fmin, m.g_fmax);
       tau[7] = m.ten0 * f - s.bias[a][7]; tau[8] = m.ten1 * f - s.bias[a][8];
       float acc = 0.f;
-      for (int k = 0; k < 9; ++k) acc += s.Minv[a][9 * r + k] * tau[k];
+      const float* Mi = s.Minv[a];
+      for (int k = 0; k < 9; ++k) acc += Mi[9 * r + k] * tau[k];
+      // warm start: arm rows, then contacts with a side on this arm
+      for (int q = 0; q < s.arow_n[a]; ++q) {
+        int code = s.arow_code[a][q]; float fq = s.arow_f[a][q];
+        if (code & 0x1000) acc += (Mi[9 * r + 7] - Mi[9 * r + 8]) * fq;
+        else { int d = code & 255; float sg = (code >> 8) ? -1.f : 1.f; acc += sg * Mi[9 * r + d] * fq; }
+      }
+      {
+        for (int c = 0; c < ncon; ++c) {
+          int cs = s.c_side[c];
+          if (!((cs >> 30) & 1)) continue;
+          const float* fc = s.c_f[c]; float mu = s.c_mu[c];
+          float l0 = fc[0] + fc[1] + fc[2] + fc[3], l1 = mu * (fc[0] - fc[1]), l2 = mu * (fc[2] - fc[3]);
+          for (int q = 0; q < 2; ++q) {
+            int sd = (cs >> (q * FM_SIDE_BITS)) & FM_SIDE_MASK;
+            if (side_type(sd) != FM_SIDE_ARM || (side_idx(sd) >> 4) != a) continue;
+            const float* Bv = s.as_B[side_slot(sd)];
+            acc += (q ? 1.f : -1.f) * (Bv[r] * l0 + Bv[9 + r] * l1 + Bv[18 + r] * l2);
+          }
+        }
+      }
       s.acc[61 + 9 * a + r] = acc;
     }
   }
 }
 
-// phase: projected Gauss-Seidel, one thread per constraint island
+// One Gauss-Seidel visit of contact c on the current acceleration: the four pyramid rows are updated in turn on the
+// contact-space acceleration u = J a (3x3 Delassus block W).  commit = false only evaluates (convergence check from the
+// warm start); commit = true stores the forces and applies Minv J^T dlam.  The belt-dof projection of the contact's force is
+// left in c_belt(c) either way (lagged belt coupling, summed by ph_belt).  Returns max |df| * A_rr.
+template <int NA> FM_HD float& c_res(EnvS<NA>& s, int c) { return s.raw_d[c][0]; }    // raw contact buffer is dead after ph_contact_setup
+template <int NA> FM_HD float& c_belt(EnvS<NA>& s, int c) { return s.raw_d[c][1]; }
 template <int NA>
-FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool first, float& belt_sum) {
+FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool commit) {
   int cs = s.c_side[c];
   f3 p = ld3(s.c_p[c]), n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); f3 t2 = cross3(n, t1);
   SideW A, B;
@@ -926,93 +977,108 @@ FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool first, f
   float f[4] = {s.c_f[c][0], s.c_f[c][1], s.c_f[c][2], s.c_f[c][3]};
   float lam[3] = {0, 0, 0};
   float maxd = 0.f;
-  if (first) {   // apply warm-start forces to the acceleration
-    lam[0] = f[0] + f[1] + f[2] + f[3]; lam[1] = mu * (f[0] - f[1]); lam[2] = mu * (f[2] - f[3]);
-  } else {
-    float u[3] = {0, 0, 0};
-    side_dot<NA>(A, n, t1, t2, &s.acc[0], &s.acc[1], &s.acc[61], u);
-    side_dot<NA>(B, n, t1, t2, &s.acc[0], &s.acc[1], &s.acc[61], u);
-    for (int r = 0; r < 4; ++r) {
-      int tq = 1 + (r >> 1); float cf = (r & 1) ? -mu : mu;
-      float Wnt = tq == 1 ? W[3] : W[4], Wtt = tq == 1 ? W[1] : W[2], Wtx = W[5];
-      float AR = W[0] + 2.f * cf * Wnt + cf * cf * Wtt + R;
-      float res = u[0] + cf * u[tq] - s.c_aref[c][r] + R * f[r];
-      float fn = fmaxf(0.f, f[r] - FM_FDIV(res, AR));
-      float df = fn - f[r];
-      f[r] = fn;
-      // contact-space acceleration update: u += W * (1, cf on tangent tq) * df
-      u[0] += (W[0] + cf * Wnt) * df;
-      u[tq] += (Wnt + cf * Wtt) * df;
-      u[3 - tq] += ((tq == 1 ? W[4] : W[3]) + cf * Wtx) * df;
-      lam[0] += df; lam[tq] += cf * df;
-      maxd = fmaxf(maxd, fabsf(df) * AR);
-    }
-    for (int r = 0; r < 4; ++r) s.c_f[c][r] = f[r];
+  float u[3] = {0, 0, 0};
+  side_dot<NA>(A, n, t1, t2, &s.acc[0], &s.acc[1], &s.acc[61], u);
+  side_dot<NA>(B, n, t1, t2, &s.acc[0], &s.acc[1], &s.acc[61], u);
+  float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
+  for (int r = 0; r < 4; ++r) {
+    int tq = 1 + (r >> 1); float cf = (r & 1) ? -mu : mu;
+    float Wnt = tq == 1 ? W[3] : W[4], Wtt = tq == 1 ? W[1] : W[2], Wtx = W[5];
+    float AR = W[0] + 2.f * cf * Wnt + cf * cf * Wtt + R;
+    float res = u[0] + cf * u[tq] - s.c_aref[c][r] + R * f[r];
+    float fn = fmaxf(0.f, f[r] - FM_FDIV(res, AR));
+    float df = fn - f[r];
+    f[r] = fn;
+    // contact-space acceleration update: u += W * (1, cf on tangent tq) * df
+    u[0] += (W[0] + cf * Wnt) * df;
+    u[tq] += (Wnt + cf * Wtt) * df;
+    u[3 - tq] += ((tq == 1 ? W[4] : W[3]) + cf * Wtx) * df;
+    lam[0] += df; lam[tq] += cf * df;
+    maxd = fmaxf(maxd, fabsf(df) * AR);
   }
-  side_apply<NA>(A, n, t1, t2, &s.acc[1], &s.acc[61], lam);
-  side_apply<NA>(B, n, t1, t2, &s.acc[1], &s.acc[61], lam);
-  // belt bookkeeping (lagged coupling): total contact-space force projected on the belt dof
+  if (commit) {
+    for (int r = 0; r < 4; ++r) s.c_f[c][r] = f[r];
+    side_apply<NA>(A, n, t1, t2, &s.acc[1], &s.acc[61], lam);
+    side_apply<NA>(B, n, t1, t2, &s.acc[1], &s.acc[61], lam);
+    Fn = f[0] + f[1] + f[2] + f[3]; F1 = mu * (f[0] - f[1]); F2 = mu * (f[2] - f[3]);
+  }
+  float bs = 0.f;
   if (A.type == FM_SIDE_BELT || B.type == FM_SIDE_BELT) {
     const SideW& o = A.type == FM_SIDE_BELT ? A : B;
-    float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
-    belt_sum += o.sgn * (o.jb[0] * Fn + o.jb[1] * F1 + o.jb[2] * F2);
+    bs = o.sgn * (o.jb[0] * Fn + o.jb[1] * F1 + o.jb[2] * F2);
   }
+  c_belt(s, c) = bs;
   return maxd;
 }
 
+// arm-local rows of arm a: mode 1 = Gauss-Seidel sweep, mode 2 = evaluate only (convergence check)
 template <int NA>
-FM_HD float arm_rows_visit(EnvS<NA>& s, int a, bool first) {
+FM_HD float arm_rows_visit(EnvS<NA>& s, int a, int mode) {
   float* acc = &s.acc[61 + 9 * a];
   float maxd = 0.f;
+  const float* Mi = s.Minv[a];
   for (int r = 0; r < s.arow_n[a]; ++r) {
     int code = s.arow_code[a][r];
     float R = s.arow_R[a][r], f = s.arow_f[a][r], df;
     if (code & 0x1000) {
-      const float* Mi = s.Minv[a];
       float AR = Mi[9 * 7 + 7] - 2.f * Mi[9 * 7 + 8] + Mi[9 * 8 + 8] + R;
-      if (first) df = f;
-      else { float res = acc[7] - acc[8] - s.arow_aref[a][r] + R * f; df = -res / AR; s.arow_f[a][r] = f + df; maxd = fmaxf(maxd, fabsf(df) * AR); }
-      for (int k = 0; k < 9; ++k) acc[k] += (Mi[9 * k + 7] - Mi[9 * k + 8]) * df;
+      float res = acc[7] - acc[8] - s.arow_aref[a][r] + R * f; df = -res / AR;
+      maxd = fmaxf(maxd, fabsf(df) * AR);
+      if (mode == 1) { s.arow_f[a][r] = f + df; for (int k = 0; k < 9; ++k) acc[k] += (Mi[9 * k + 7] - Mi[9 * k + 8]) * df; }
     } else {
       int d = code & 255; float sg = (code >> 8) ? -1.f : 1.f;
-      const float* Mi = s.Minv[a];
       float AR = Mi[9 * d + d] + R;
-      if (first) df = f;
-      else { float res = sg * acc[d] - s.arow_aref[a][r] + R * f; float fn = fmaxf(0.f, f - res / AR); df = fn - f; s.arow_f[a][r] = fn; maxd = fmaxf(maxd, fabsf(df) * AR); }
-      for (int k = 0; k < 9; ++k) acc[k] += sg * Mi[9 * k + d] * df;
+      float res = sg * acc[d] - s.arow_aref[a][r] + R * f; float fn = fmaxf(0.f, f - res / AR); df = fn - f;
+      maxd = fmaxf(maxd, fabsf(df) * AR);
+      if (mode == 1) { s.arow_f[a][r] = fn; for (int k = 0; k < 9; ++k) acc[k] += sg * Mi[9 * k + d] * df; }
     }
   }
   return maxd;
 }
 
+// phase: convergence check of the warm start, one lane per contact (evaluation only; nothing another lane reads is written)
+template <int NA, int E>
+FM_HD void ph_check(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
+  for (int w = tid; w < FM_MAXCON * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int c = w / E;
+    if (c >= s.ncon) continue;
+    c_res(s, c) = contact_visit(s, m, c, false);
+  }
+}
+
+// phase: projected Gauss-Seidel, one lane per constraint island.  Islands whose warm start already satisfies the stopping
+// criterion (every row's update below tol, the steady state of resting contacts) are left as they are.
 template <int NA, int E>
 FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < NN * E; w += T) {
     EnvS<NA>& s = S[w % E]; int node = w / E;
-    s.belt_part[node] = 0.f;
     if (s.isl_root[node] != node) continue;
     int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
-    bool has_arm = false;
-    for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
+    bool has_arm = false, single_row = true;
+    for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) { has_arm = true; single_row = single_row && s.arow_n[a] == 1; }
     if (c0 == c1 && !has_arm) continue;
-    float belt_sum = 0.f;
-    // warm start: apply the previous solve's forces
-    for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) arm_rows_visit(s, a, true);
-    for (int ci = c0; ci < c1; ++ci) contact_visit(s, m, s.isl_list[ci], true, belt_sum);
+    float maxd = 0.f;
+    for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, 2));
+    for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, c_res(s, s.isl_list[ci]));
     FM_DBG(fm_dbg_islands++;)
-    // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
-    // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236)
-    const int cap = (has_arm && c1 > c0) ? 8 * inner : inner;
-    for (int it = 0; it < cap; ++it) {
-      float maxd = 0.f; belt_sum = 0.f;
-      FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0;)
-      for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, false));
-      for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, contact_visit(s, m, s.isl_list[ci], false, belt_sum));
-      if (maxd < tol) break;
+    FM_DBG(int dbg_kind = has_arm ? (c1 > c0 ? 2 : 1) : 0; int dbg_sw = 0; fm_dbg_cnt[4 + 4 * dbg_kind]++; fm_dbg_cnt[7 + 4 * dbg_kind] += c1 - c0;)
+    if (maxd >= tol) {
+      // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
+      // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236);
+      // a lone arm with only its plate equality row is solved exactly by one visit
+      const int cap = (has_arm && c1 > c0) ? 8 * inner : ((c1 == c0 && single_row) ? 1 : inner);
+      for (int it = 0; it < cap; ++it) {
+        maxd = 0.f;
+        FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0; dbg_sw++; fm_dbg_cnt[5 + 4 * dbg_kind]++; fm_dbg_cnt[6 + 4 * dbg_kind] += c1 - c0;)
+        for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, 1));
+        for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, contact_visit(s, m, s.isl_list[ci], true));
+        if (maxd < tol) break;
+      }
     }
-    s.belt_part[node] = belt_sum;
+    FM_DBG(fm_dbg_cnt[16 + (dbg_sw < 9 ? dbg_sw : 9)] += (dbg_kind == 0);)
   }
 }
 
@@ -1024,7 +1090,7 @@ FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
     float sum = 0.f;
-    for (int i = 0; i < EnvS<NA>::NNODE; ++i) sum += s.belt_part[i];
+    for (int c = 0; c < s.ncon; ++c) sum += c_belt(s, c);
     s.belt_S = sum / m.belt_mass;
     s.acc[0] = s.belt_acc_smooth + s.belt_S;
   }

@@ -73,7 +73,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
   int N = st.n;
   for (int w = tid; w < L::NF * E; w += T) {
     int e = w % E, fidx = w / E; int env = env0 + e;
-    if (env >= N) continue;
+    if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     EnvS<NA>& s = S[e];
     float v = st.f[(size_t)fidx * N + env];
     if (fidx == L::F_BELT_Q) s.belt_q = v;
@@ -94,7 +94,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
   }
   for (int w = tid; w < L::NI * E; w += T) {
     int e = w % E, k = w / E; int env = env0 + e;
-    if (env >= N) continue;
+    if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     int v = st.i[(size_t)k * N + env];
     TaskS& t = TS[e];
     if (k == L::I_PREV_N) S[e].prev_n = v;
@@ -112,13 +112,13 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
   }
   for (int w = tid; w < E; w += T) {
     int env = env0 + w;
-    if (env >= N) continue;
+    float* ws = st.ws + (size_t)env * FM_WS_FLOATS;    // the scratch has rows for the padding slots too
+    if (env >= N) env = N - 1;
     TS[w].conveyor_speed = st.d[(size_t)L::D_CONV * N + env];
     TS[w].spawn_freq = st.d[(size_t)L::D_SPAWN_FREQ * N + env];
     TS[w].play_time = st.d[(size_t)L::D_PLAY_TIME * N + env];
     S[w].conveyor_speed = (float)TS[w].conveyor_speed;
     S[w].flags = 0; S[w].force_max = 0.f;
-    float* ws = st.ws + (size_t)env * FM_WS_FLOATS;
     S[w].as_J = reinterpret_cast<float (*)[27]>(ws);
     S[w].as_B = reinterpret_cast<float (*)[27]>(ws + FM_MAXARMSIDE * 27);
     S[w].prev_f = reinterpret_cast<float (*)[4]>(ws + FM_MAXARMSIDE * 54);
@@ -133,7 +133,7 @@ FM_HD void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid,
   int N = st.n;
   for (int w = tid; w < 130 * E; w += T) {
     int e = w % E, k = w / E; int env = env0 + e;
-    if (env >= N) continue;
+    if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     if (k < 70) (&S[e].cube_q[0][0])[k] = st.f[(size_t)(L::F_CUBE_Q + k) * N + env];
     else (&S[e].cube_v[0][0])[k - 70] = st.f[(size_t)(L::F_CUBE_V + k - 70) * N + env];
   }

@@ -14,12 +14,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 _lib = None
 
 
+_STEP_HDRS = ["fm_types.h", "fm_math.cuh", "fm_collide.cuh", "fm_step.cuh", "fm_task.cuh", "fm_driver.cuh", "fm_kernel.cuh"]
+_SHAPES = ["2_1", "2_4", "2_14", "4_1", "4_4", "4_7"]        # arms _ envs per block (fm_kernel.cuh)
 _DEPS = {
-    "fm_lib.cu": ["fm_lib.cu", "fm_types.h", "fm_math.cuh", "fm_collide.cuh", "fm_step.cuh", "fm_task.cuh", "fm_driver.cuh", "fm_ik.cuh",
-                  "fm_host_model.h", "fm_host_common.h", "../../include/fm_api.h", "../../include/fm_blob.h"],
+    "fm_lib.cu": ["fm_lib.cu", "fm_ik.cuh", "fm_host_model.h", "fm_host_common.h", "../../include/fm_api.h", "../../include/fm_blob.h"] + _STEP_HDRS,
     "fm_ppo.cu": ["fm_ppo.cu", "../../include/fm_api.h"],
     "fm_mlp_tc5.cu": ["fm_mlp_tc5.cu"],
 }
+for _s in _SHAPES:
+    _DEPS[f"fm_step_shape_{_s}.cu"] = [f"fm_step_shape_{_s}.cu"] + _STEP_HDRS
 
 
 def _newer(target: str, deps) -> bool:
@@ -29,23 +32,27 @@ def _newer(target: str, deps) -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc cross-compiles for sm_100a without a GPU (used by __graft_entry__.build()).  One object per .cu so that a
-    change to the PPO kernels does not recompile the (large, fully inlined) step kernel."""
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = SO_PATH, objdir: str | None = None) -> str:
+    """nvcc cross-compiles for sm_100a without a GPU (used by __graft_entry__.build()).  One object per .cu, compiled in
+    parallel: the fused step kernel is fully inlined (~50 k SASS lines per block shape), so every shape is its own
+    translation unit.  extra_flags / out / objdir: kernel-variant experiments (tools/ab_variant.py)."""
+    from concurrent.futures import ThreadPoolExecutor
     src = os.path.join(_HERE, "csrc")
-    bdir = os.path.join(src, "build")
+    bdir = objdir or os.path.join(src, "build")
     os.makedirs(bdir, exist_ok=True)
-    objs, relink = [], force
+    objs, jobs = [], []
     for cu, deps in _DEPS.items():
         obj = os.path.join(bdir, cu.replace(".cu", ".o"))
         if force or _newer(obj, [os.path.join(src, d) for d in deps]):
-            cmd = ["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(src, cu)]
-            subprocess.check_call(cmd)
-            relink = True
+            jobs.append(["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+                        + ["-c", "-o", obj, os.path.join(src, cu)])
         objs.append(obj)
-    if relink or _newer(SO_PATH, objs):
-        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs)
-    return SO_PATH
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(subprocess.check_call, jobs))
+    if jobs or _newer(out, objs):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return out
 
 
 def load() -> C.CDLL:
@@ -54,7 +61,8 @@ def load() -> C.CDLL:
         if not os.path.exists(SO_PATH):
             raise RuntimeError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(the CUDA extension is required; there is no CPU path)")
-        _lib = _capi.bind(C.CDLL(SO_PATH))
+        # FM_B200_LIB: kernel-variant A/B experiments only (tools/ab_variant.sh); the product loads the in-tree library
+        _lib = _capi.bind(C.CDLL(os.environ.get("FM_B200_LIB") or SO_PATH))
         _lib.fm_launch_count.restype = C.c_longlong
         _lib.fm_launch_count.argtypes = [C.c_void_p]
     return _lib

@@ -42,7 +42,7 @@ static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
   }
 }
 static void dispatch(fm_handle* h, const FmStepArgs& ar) {
-  if (h->hm.n_arms == 2) { if (h->E == 1) run_blocks<2, 1>(h, ar); else if (h->E == 2) run_blocks<2, 2>(h, ar); else run_blocks<2, 4>(h, ar); }
+  if (h->hm.n_arms == 2) { if (h->E == 1) run_blocks<2, 1>(h, ar); else if (h->E == 2) run_blocks<2, 2>(h, ar); else if (h->E == 7) run_blocks<2, 7>(h, ar); else run_blocks<2, 4>(h, ar); }
   else { if (h->E == 1) run_blocks<4, 1>(h, ar); else run_blocks<4, 4>(h, ar); }
 }
 
@@ -80,6 +80,7 @@ extern "C" int fm_emu_check_box_on_face(int n, unsigned long long seed, int* app
 extern "C" {
 void fm_emu_set_order(int o) { g_order = o; }
 void fm_emu_counters(long long* o) { o[0] = fm_dbg_sweeps; o[1] = fm_dbg_visits; o[2] = fm_dbg_islands; }
+void fm_emu_counters2(long long* o) { for (int i = 0; i < 32; ++i) o[i] = fm_dbg_cnt[i]; }
 const char* fm_last_error(void) { return g_err.c_str(); }
 int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {
   try {
@@ -88,8 +89,8 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
-    h->E = (cfg->envs_per_block == 1 || cfg->envs_per_block == 2) ? cfg->envs_per_block : 4;
-    h->ws.assign((size_t)cfg->n_envs * FM_WS_FLOATS, 0.f);
+    h->E = (cfg->envs_per_block == 1 || cfg->envs_per_block == 2 || (cfg->envs_per_block == 7 && cfg->n_arms == 2)) ? cfg->envs_per_block : 4;
+    h->ws.assign(((size_t)cfg->n_envs + 32) * FM_WS_FLOATS, 0.f);
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, h->ws.data()};
     *out = h; return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }

@@ -93,3 +93,25 @@ def test_box_on_face_fast_path_equals_general_box_box():
     applied = C.c_int()
     bad = emu_lib().fm_emu_check_box_on_face(200000, C.c_ulonglong(2024), C.byref(applied))
     assert applied.value > 100000 and bad == 0, (bad, applied.value)
+
+
+def test_golden_rollouts_block_of_7_with_padding_slots():
+    """E = 7 envs per block with 4 envs: three padding slots step a copy of the last env and store nothing."""
+    pc.case_golden_rollouts(BE, 2, ["AllFullRLProgressRewardEnv"], envs_per_block=7)
+
+
+def test_block_shapes_agree():
+    """the per-env result does not depend on how envs are grouped into blocks (E = 1, 4, 7; 5 envs -> ragged last block)"""
+    from factory_marl_b200 import model as fm
+    blob = fm.build_blob(2)
+    outs = []
+    for E in (1, 4, 7):
+        core = make_core(blob, 5, 2, "AllFullRLProgressRewardEnv", seeds=list(range(42, 47)), auto_reset=True, envs_per_block=E, **pc.PROGRESS_KW)
+        core.reset()
+        rng = np.random.default_rng(3)
+        for t in range(12):
+            core.env_step(np.clip(rng.standard_normal((5, 16)), -1, 1).astype(np.float32))
+        outs.append((np.array(core.obs), np.array(core.reward), np.array(core.f)))
+    for o in outs[1:]:
+        assert np.allclose(o[0], outs[0][0], rtol=0, atol=1e-6) and np.allclose(o[1], outs[0][1], atol=1e-6)
+        assert np.allclose(o[2], outs[0][2], rtol=0, atol=1e-5)

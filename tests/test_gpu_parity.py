@@ -78,7 +78,8 @@ def test_full_size_properties_4096_envs():
     acts = [(torch.rand((4096, 16), device="cuda", generator=gen) * 2 - 1) * 0.4 for _ in range(12)]
 
     def run(n):
-        env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=n, num_arms=2, seeds=list(range(42, 42 + n)), **kw)
+        # 4096 envs select the one-block-per-SM shape (14 envs per block); the small batch is pinned to the same shape
+        env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=n, num_arms=2, seeds=list(range(42, 42 + n)), envs_per_block=14, **kw)
         env.reset()
         out = []
         for a in acts:
@@ -103,6 +104,28 @@ def test_full_size_properties_4096_envs():
     assert ((qn - 1).abs() < 1e-4).float().mean() > 0.85
     assert (env.core.i[env.core.off("I_NIN")] + env.core.i[env.core.off("I_NOUT")] == 10).all()
     assert env.gpu_launches >= 13
+
+
+@pytest.mark.parametrize("n_arms,shapes", [(2, (1, 4, 14)), (4, (4, 7))])
+def test_block_shapes_agree(n_arms, shapes):
+    """every block shape built into the library (envs per block / warps per block) steps the same env to the same result;
+    17 envs leave a ragged last block whose padding slots must not leak"""
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    kw = dict(gripper_to_closest_cube_reward_factor=0.2, closest_cube_to_bucket_reward_factor=0.4, base_reward=0.4)
+    n = 17
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = [torch.randn((n, 8 * n_arms), device="cuda", generator=gen).clamp(-1, 1) for _ in range(10)]
+    outs = []
+    for E in shapes:
+        env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=n, num_arms=n_arms, seeds=list(range(7, 7 + n)), envs_per_block=E, **kw)
+        env.reset()
+        for a in acts:
+            obs, rew, term, _ = env.step(a)
+        assert int(env.core.i[env.core.off("I_FLAGS")].max()) == 0
+        outs.append((obs.clone(), rew.clone(), env.core.i[env.core.off("I_NIN")].clone()))
+    for o in outs[1:]:
+        assert torch.allclose(o[0], outs[0][0], rtol=0, atol=2e-4), float((o[0] - outs[0][0]).abs().max())
+        assert torch.allclose(o[1], outs[0][1], rtol=0, atol=2e-4) and torch.equal(o[2], outs[0][2])
 
 
 def test_auto_reset_and_episode_info():
