@@ -181,14 +181,16 @@ FM_HD int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 B
 }
 
 // Fast path of col_box_box for a small box resting on / falling onto the top face of a big AXIS-ALIGNED box (belt, table,
-// bucket floor): when the small box's bounding sphere lies horizontally inside the top face and its centre is above it,
+// bucket floor): when the small box's vertices all lie horizontally inside the top face and its centre is above it,
 // the separating-axis search of col_box_box always selects the big box's +z face (see tests: fm_emu_check_box_on_face),
 // no clipping happens, and the contacts are the vertices of the incident face below the surface, in the same order.
 // `big_is_1`: the big box is geom1 (normal +z) or geom2 (normal -z).  Returns -1 when the fast path does not apply.
 FM_HD int col_box_on_face(f3 pb, f3 hb, f3 pc, const float* Rc, f3 hc, bool big_is_1, RawC* out) {
   float r = norm3(hc);
   float top = pb.z + hb.z;
-  if (!(fminf(hb.x, hb.y) >= 0.25f) || pc.z < top || fabsf(pc.x - pb.x) + r > hb.x || fabsf(pc.y - pb.y) + r > hb.y) return -1;
+  // horizontal half-extents of the small box (exact projection of its vertices on the big box's x / y axes)
+  float ex = fabsf(Rc[0]) * hc.x + fabsf(Rc[1]) * hc.y + fabsf(Rc[2]) * hc.z, ey = fabsf(Rc[3]) * hc.x + fabsf(Rc[4]) * hc.y + fabsf(Rc[5]) * hc.z;
+  if (!(fminf(hb.x, hb.y) >= 0.25f) || pc.z < top || fabsf(pc.x - pb.x) + ex * 1.0001f > hb.x || fabsf(pc.y - pb.y) + ey * 1.0001f > hb.y) return -1;
   if (pc.z - r > top) return 0;
   f3 nr = mk3(0, 0, 1);
   int iax = 0; float mn = 1e30f, isg = 1.f;

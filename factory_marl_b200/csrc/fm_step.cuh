@@ -36,6 +36,7 @@ static inline int fm_host_max(int* p, int v) { int o = *p; *p = o > v ? o : v; r
 #if !defined(__CUDACC__)
 static long long fm_dbg_sweeps = 0, fm_dbg_visits = 0, fm_dbg_islands = 0;   // host logic-test build only
 static long long fm_dbg_cnt[32] = {0};
+static long long fm_dbg_sat[512] = {0};   // general SAT calls by geom1
 #define FM_DBG(x) x
 #else
 #define FM_DBG(x)
@@ -523,7 +524,8 @@ FM_HD void pair_box_box(EnvS<NA>& s, const GeomBox& x, const GeomBox& y, bool ar
     if (nf >= 0) { FM_DBG(fm_dbg_cnt[27]++;) emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rf, nf); return; }
   }
   if (far_sphere_box(g2.p, norm3(g2.hs), g1.p, g1.R, g1.hs) || far_sphere_box(g1.p, norm3(g1.hs), g2.p, g2.R, g2.hs)) { FM_DBG(fm_dbg_cnt[28]++;) return; }
-  FM_DBG(fm_dbg_cnt[29]++; fm_dbg_cnt[30] += armgeom;)
+  FM_DBG(fm_dbg_cnt[29]++; fm_dbg_cnt[30] += armgeom; fm_dbg_sat[g1.geom & 511]++;)
+  FM_DBG(if (g1.geom == 2) { float r = norm3(g2.hs); float top = g1.p.z + g1.hs.z; int why = g2.p.z < top ? 0 : (fabsf(g2.p.x - g1.p.x) + r > g1.hs.x ? 1 : (fabsf(g2.p.y - g1.p.y) + r > g1.hs.y ? 2 : 3)); fm_dbg_sat[200 + why]++; if (why == 1) fm_dbg_sat[210 + (int)fminf(9.f, fabsf(g2.p.x - g1.p.x) * 20.f)]++; })
   RawC rc[8];
   int n = col_box_box(g1.p, g1.R, g1.hs, g2.p, g2.R, g2.hs, rc);
   emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rc, n);

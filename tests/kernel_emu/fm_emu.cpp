@@ -80,6 +80,7 @@ extern "C" int fm_emu_check_box_on_face(int n, unsigned long long seed, int* app
 extern "C" {
 void fm_emu_set_order(int o) { g_order = o; }
 void fm_emu_counters(long long* o) { o[0] = fm_dbg_sweeps; o[1] = fm_dbg_visits; o[2] = fm_dbg_islands; }
+void fm_emu_sat(long long* o) { for (int i = 0; i < 512; ++i) o[i] = fm_dbg_sat[i]; }
 void fm_emu_counters2(long long* o) { for (int i = 0; i < 32; ++i) o[i] = fm_dbg_cnt[i]; }
 const char* fm_last_error(void) { return g_err.c_str(); }
 int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {

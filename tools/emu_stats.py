@@ -31,3 +31,6 @@ for k, nm in enumerate(["cube-only", "arm-only", "arm+contacts"]):
     print("%-13s islands/substep %.3f sweeps/island %.2f contacts/island %.2f sweep-visits/substep %.2f" % (nm, isl / ss, sw / max(isl, 1), con / max(isl, 1), vis / ss))
 print("cube-only sweep histogram", (c[16:26] / max(c[16:26].sum(), 1)).round(3))
 print("box-box per substep: fast path %.3f, far-sphere reject %.3f, general SAT %.3f (with an arm geom %.3f)" % (c[27] / ss, c[28] / ss, c[29] / ss, c[30] / ss))
+o = (C.c_longlong * 512)(); lib.fm_emu_sat.argtypes = [C.c_void_p]; lib.fm_emu_sat(o)
+sat = np.array(list(o)); names = model.assemble(2)["geom_names"] if hasattr(model, "assemble") else None
+print("general SAT by geom1 id (whole run):", {int(k): int(sat[k]) for k in np.nonzero(sat)[0]})
