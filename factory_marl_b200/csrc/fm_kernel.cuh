@@ -6,6 +6,18 @@
 #include <cuda_runtime.h>
 #include "fm_driver.cuh"
 
+// the one-block-per-SM shape of the two-arm / four-arm scene (overridable for shape experiments, tools/ab_variant.py)
+#ifndef FM_BIG2_E
+#define FM_BIG2_E 14
+#define FM_BIG2_TW 12
+#endif
+#ifndef FM_BIG4_E
+#define FM_BIG4_E 7
+#define FM_BIG4_TW 7
+#endif
+#ifndef FM_MINBLK
+#define FM_MINBLK 1
+#endif
 struct FmLaunch { const FmDevModel* model; const unsigned int* cpairs; const int* geom_class; FmEnvCfg cfg; FmStatePtrs st; };
 
 template <int NA, int E, int TW>
@@ -18,7 +30,7 @@ struct DevRun {
 };
 
 template <int NA, int E, int TW>
-__global__ void __launch_bounds__(32 * TW, 1) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned int* __restrict__ cpairs,
+__global__ void __launch_bounds__(32 * TW, FM_MINBLK) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned int* __restrict__ cpairs,
                                                              const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvS<NA>* S = reinterpret_cast<EnvS<NA>*>(smem_raw);
@@ -51,8 +63,8 @@ cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t
 #else
 extern template cudaError_t fm_launch_step<2, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<2, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
-extern template cudaError_t fm_launch_step<2, 14, 12>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
-extern template cudaError_t fm_launch_step<4, 7, 7>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 #endif

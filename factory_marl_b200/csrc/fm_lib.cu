@@ -37,8 +37,8 @@ static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
   FmLaunch L{h->d_model, h->d_cpairs, h->d_geom_class, h->cfg, h->st};
   cudaError_t e;
-  if (h->hm.n_arms == 2) e = h->E == 14 ? fm_launch_step<2, 14, 12>(L, ar, s) : (h->E == 1 ? fm_launch_step<2, 1, 1>(L, ar, s) : fm_launch_step<2, 4, 4>(L, ar, s));
-  else e = h->E == 7 ? fm_launch_step<4, 7, 7>(L, ar, s) : (h->E == 1 ? fm_launch_step<4, 1, 1>(L, ar, s) : fm_launch_step<4, 4, 4>(L, ar, s));
+  if (h->hm.n_arms == 2) e = h->E == FM_BIG2_E ? fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW>(L, ar, s) : (h->E == 1 ? fm_launch_step<2, 1, 1>(L, ar, s) : fm_launch_step<2, 4, 4>(L, ar, s));
+  else e = h->E == FM_BIG4_E ? fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(L, ar, s) : (h->E == 1 ? fm_launch_step<4, 1, 1>(L, ar, s) : fm_launch_step<4, 4, 4>(L, ar, s));
   if (e != cudaSuccess) { g_err = std::string("fm_step_kernel launch: ") + cudaGetErrorString(e); return 2; }
   h->launches++;
   return 0;
@@ -58,9 +58,9 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (cfg->env_class < 0 || cfg->env_class > 6) throw std::runtime_error("bad env_class");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
     // envs per block: 1 | 4 | the one-block-per-SM shape (14 with two arms, 7 with four); 0 = by batch size
-    const int big = h->hm.n_arms == 2 ? 14 : 7;
+    const int big = h->hm.n_arms == 2 ? FM_BIG2_E : FM_BIG4_E;
     int E = cfg->envs_per_block;
-    h->E = (E == 1 || E == 4 || E == big) ? E : (cfg->n_envs >= 148 * big ? big : 4);
+    h->E = (E == 1 || E == 4 || E == big) ? E : (cfg->n_envs >= 2048 ? big : 4);
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, nullptr};
     FM_CUDA(cudaMalloc(&h->d_model, sizeof(FmDevModel)));
     FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));

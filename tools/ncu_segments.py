@@ -21,3 +21,19 @@ print(f"total samples {ts} total warp-inst {ti} ({ti/nblk/nsub:.0f} per sub-step
 for k, s in enumerate(segs):
     if s['samp'] > 0.003 * ts or s['inst'] > 0.003 * ti:
         print(f"seg {k:3d} sass {s['n']:6d} samp {100*s['samp']/ts:5.1f}% (barrier {100*s['bar']/max(1,s['samp']):3.0f}%) inst {100*s['inst']/ti:5.1f}% ({s['inst']/nblk/nsub:7.0f}/substep/CTA) thr/inst {s['thr']/max(1,s['inst']):5.1f} local {100*s['ldl']/max(1,s['inst']):4.1f}% glob {100*s['ldg']/max(1,s['inst']):4.1f}%")
+
+# Lock-step blocks: samples with stall_barrier sit on the instruction AFTER a BAR.SYNC, i.e. they are the wait for the slowest
+# lane of the PREVIOUS interval.  Second table: per interval, own work samples vs the wait that follows it.
+print("\nwork vs barrier wait (wait = stall_barrier samples at the start of the next segment, attributed back):")
+seg2 = []; cur = dict(work=0, wait=0, inst=0)
+for r in data:
+    b = int(r[ibar]); cur['work'] += int(r[isamp]) - b; cur['wait'] += b; cur['inst'] += int(r[iinst])
+    if 'BAR.SYNC' in r[ia]:
+        seg2.append(cur); cur = dict(work=0, wait=0, inst=0)
+seg2.append(cur)
+tw = sum(x['wait'] for x in seg2)
+print(f"barrier wait total {100*tw/ts:.1f}% of samples")
+for k in range(len(seg2) - 1):
+    w_after = seg2[k + 1]['wait']
+    if seg2[k]['work'] + w_after > 0.004 * ts:
+        print(f"seg {k:3d} work {100*seg2[k]['work']/ts:5.1f}%  wait for its slowest lane {100*w_after/ts:5.1f}%  inst {seg2[k]['inst']/nblk/nsub:7.0f}/substep/CTA")
