@@ -453,9 +453,10 @@ template <int NA, int E>
 FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int np = m.n_cluster_pair, s0 = m.cl_sph0;
-  EnvS<NA>& s = S[tid % E];                              // T is a multiple of E: a thread always serves the same env
+  const int stride = T / E;                              // lanes per env; a lane always serves the same env
+  if (tid >= stride * E) return;                         // T need not be a multiple of E: the remainder lanes sit this phase out
+  EnvS<NA>& s = S[tid % E];
   const bnd4* bnd = reinterpret_cast<const bnd4*>(&s.bnd[0][0]) - s0;
-  const int stride = T / E;
   for (int p0 = tid / E; p0 < np; p0 += 4 * stride) {
     // four pair records are fetched up front so their global-load latencies overlap
     unsigned recs[4];
@@ -465,6 +466,7 @@ FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __rest
     for (int u = 0; u < 4; ++u) {
       unsigned rec = recs[u];
       if (rec == 0xFFFFFFFFu) continue;
+      FM_DBG(fm_dbg_cnt[31]++;)
       int c1 = rec & 255, c2 = (rec >> 8) & 255, type = rec >> 16;
       bnd4 b2 = bnd[c2];
       bool far;

@@ -29,21 +29,21 @@ struct fm_handle {
   std::vector<char> smem; std::vector<float> ws;
 };
 
-template <int NA, int E>
+template <int NA, int E, int TW = E>
 static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
-  HostRun run{32 * E};
+  HostRun run{32 * TW};
   size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS)) + 64;
   if (h->smem.size() < need) h->smem.resize(need);
   int nblk = (h->cfg.n_envs + E - 1) / E;
   for (int b = 0; b < nblk; ++b) {
     memset(h->smem.data(), 0, need);
     EnvS<NA>* S = (EnvS<NA>*)h->smem.data(); TaskS* TS = (TaskS*)(S + E);
-    fm_block_step<NA, E>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
+    fm_block_step<NA, E, TW>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
   }
 }
 static void dispatch(fm_handle* h, const FmStepArgs& ar) {
-  if (h->hm.n_arms == 2) { if (h->E == 1) run_blocks<2, 1>(h, ar); else if (h->E == 2) run_blocks<2, 2>(h, ar); else if (h->E == 7) run_blocks<2, 7>(h, ar); else run_blocks<2, 4>(h, ar); }
-  else { if (h->E == 1) run_blocks<4, 1>(h, ar); else run_blocks<4, 4>(h, ar); }
+  if (h->hm.n_arms == 2) { if (h->E == 1) run_blocks<2, 1>(h, ar); else if (h->E == 2) run_blocks<2, 2>(h, ar); else if (h->E == 7) run_blocks<2, 7>(h, ar); else if (h->E == 14) run_blocks<2, 14, 12>(h, ar); else run_blocks<2, 4>(h, ar); }
+  else { if (h->E == 1) run_blocks<4, 1>(h, ar); else if (h->E == 7) run_blocks<4, 7, 7>(h, ar); else run_blocks<4, 4>(h, ar); }
 }
 
 // randomised equivalence check of the box-on-face fast path against the general separating-axis routine
@@ -90,7 +90,7 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
-    h->E = (cfg->envs_per_block == 1 || cfg->envs_per_block == 2 || (cfg->envs_per_block == 7 && cfg->n_arms == 2)) ? cfg->envs_per_block : 4;
+    { int e = cfg->envs_per_block; h->E = (e == 1 || e == 7 || (cfg->n_arms == 2 && (e == 2 || e == 14))) ? e : 4; }   // same shapes as the library (+ E = 2)
     h->ws.assign(((size_t)cfg->n_envs + 32) * FM_WS_FLOATS, 0.f);
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, h->ws.data()};
     *out = h; return 0;

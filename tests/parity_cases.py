@@ -55,7 +55,7 @@ def case_single_substep_free(be, n_arms=2):
     assert rel(gq, q2) < 1e-6 and rel(gv, v2) < 1e-4, (rel(gq, q2), rel(gv, v2))
 
 
-def case_single_substep_contacts(be):
+def case_single_substep_contacts(be, **extra):
     """settled scene (cube riding the belt, 9 hidden cubes on the floor): contact pair set bit-exact, then one sub-step."""
     blob = fm.build_blob(2)
     g = np.load(GOLDEN + "/known_answers.npz")
@@ -63,7 +63,7 @@ def case_single_substep_contacts(be):
     o = Oracle(blob)
     ctrl = np.zeros(17); ctrl[0] = -0.112; ctrl[8] = 0.03; ctrl[16] = 0.03
     o.set_state(q, v); o.step1()
-    core = be.mk(blob, 4, 2, "AllFullRLProgressRewardEnv", auto_reset=False, **CONVERGED)
+    core = be.mk(blob, 4, 2, "AllFullRLProgressRewardEnv", auto_reset=False, **CONVERGED, **extra)
     core.reset(); core.set_state(0, q, v, ctrl)
     d = core.debug_substeps(1, env=0)
     og, ocd = o.contacts()

@@ -32,6 +32,11 @@ def test_single_substep_contacts_pairset_bit_exact():
     pc.case_single_substep_contacts(BE)
 
 
+def test_single_substep_contacts_pairset_one_block_per_sm_shape():
+    """14 envs on 12 warps: the lane count is not a multiple of the env count (every cluster pair must be visited once)"""
+    pc.case_single_substep_contacts(BE, envs_per_block=14)
+
+
 def test_golden_rollouts_2arms():
     pc.case_golden_rollouts(BE, 2)
 
@@ -101,11 +106,12 @@ def test_golden_rollouts_block_of_7_with_padding_slots():
 
 
 def test_block_shapes_agree():
-    """the per-env result does not depend on how envs are grouped into blocks (E = 1, 4, 7; 5 envs -> ragged last block)"""
+    """the per-env result does not depend on how envs are grouped into blocks (E = 1, 4, 7, and 14 envs on 12 warps: a lane
+    count that is not a multiple of E; 5 envs -> ragged last block)"""
     from factory_marl_b200 import model as fm
     blob = fm.build_blob(2)
     outs = []
-    for E in (1, 4, 7):
+    for E in (1, 4, 7, 14):
         core = make_core(blob, 5, 2, "AllFullRLProgressRewardEnv", seeds=list(range(42, 47)), auto_reset=True, envs_per_block=E, **pc.PROGRESS_KW)
         core.reset()
         rng = np.random.default_rng(3)
@@ -115,3 +121,26 @@ def test_block_shapes_agree():
     for o in outs[1:]:
         assert np.allclose(o[0], outs[0][0], rtol=0, atol=1e-6) and np.allclose(o[1], outs[0][1], atol=1e-6)
         assert np.allclose(o[2], outs[0][2], rtol=0, atol=1e-5)
+
+
+def test_broad_phase_visits_every_pair_once():
+    """lane -> (env, pair) mapping of the broad phase: every env slot of a block visits every admissible cluster pair exactly
+    once per sub-step, also when the lane count (12 warps) is not a multiple of the envs per block (14)"""
+    import ctypes as C
+    from factory_marl_b200 import model as fm
+    from tests.emu_backend import emu_lib
+    blob = fm.build_blob(2)
+    lib = emu_lib(); lib.fm_emu_counters2.argtypes = [C.c_void_p]
+
+    def visits():
+        o = (C.c_longlong * 32)(); lib.fm_emu_counters2(o); return o[31]
+    per_slot = {}
+    for E, slots in [(1, 4), (4, 4), (7, 7), (14, 14)]:
+        core = make_core(blob, 4, 2, "AllFullRLProgressRewardEnv", auto_reset=False, envs_per_block=E)
+        core.reset()
+        v0 = visits()
+        core.debug_substeps(3, env=0)
+        per_slot[E] = (visits() - v0) / (3 * slots)
+    n_pairs = per_slot[1]
+    assert 600 < n_pairs < 900 and n_pairs == int(n_pairs)
+    assert all(v == n_pairs for v in per_slot.values()), per_slot

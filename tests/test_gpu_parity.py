@@ -42,6 +42,11 @@ def test_single_substep_contacts_pairset_bit_exact():
     pc.case_single_substep_contacts(BE)
 
 
+def test_single_substep_contacts_pairset_one_block_per_sm_shape():
+    """14 envs on 12 warps: the lane count is not a multiple of the env count (every cluster pair must be visited once)"""
+    pc.case_single_substep_contacts(BE, envs_per_block=14)
+
+
 def test_golden_rollouts_2arms():
     pc.case_golden_rollouts(BE, 2)
 
