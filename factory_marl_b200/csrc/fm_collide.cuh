@@ -94,19 +94,32 @@ FM_HD int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 B
     if (s > best + 1e-6f) { best = s; code = 3 + j; flip = e < 0.f; nbest = rcol(R2, j); }
   }
   const float fudge = 1.05f;
-  for (int i = 0; i < 3; ++i)
+  // edge axes a_i x b_j in closed form (box-1 frame): |a_i x b_j|^2 = 1 - R_ij^2, projections from R, |R| and pp
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
     for (int j = 0; j < 3; ++j) {
-      f3 ax = cross3(rcol(R1, i), rcol(R2, j));
-      float l = norm3(ax);
-      if (l < 1e-4f) continue;
-      ax = ax * (1.0f / l);
-      float e = dot3(ax, pw);
-      float ra = A.x * fabsf(dot3(ax, rcol(R1, 0))) + A.y * fabsf(dot3(ax, rcol(R1, 1))) + A.z * fabsf(dot3(ax, rcol(R1, 2)));
-      float rb = B.x * fabsf(dot3(ax, rcol(R2, 0))) + B.y * fabsf(dot3(ax, rcol(R2, 1))) + B.z * fabsf(dot3(ax, rcol(R2, 2)));
-      float s = fabsf(e) - (ra + rb);
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      float l2 = 1.f - R[3 * i + j] * R[3 * i + j], e, s;
+      if (l2 < 0.02f) {      // nearly parallel edges: 1 - R^2 cancels in fp32, take the axis itself
+        f3 ax = cross3(rcol(R1, i), rcol(R2, j));
+        float l = norm3(ax);
+        if (l < 1e-4f) continue;
+        ax = ax * (1.0f / l);
+        e = dot3(ax, pw);
+        float ra = A.x * fabsf(dot3(ax, rcol(R1, 0))) + A.y * fabsf(dot3(ax, rcol(R1, 1))) + A.z * fabsf(dot3(ax, rcol(R1, 2)));
+        float rb = B.x * fabsf(dot3(ax, rcol(R2, 0))) + B.y * fabsf(dot3(ax, rcol(R2, 1))) + B.z * fabsf(dot3(ax, rcol(R2, 2)));
+        s = fabsf(e) - (ra + rb);
+      } else {
+        e = comp3(pp, i2) * R[3 * i1 + j] - comp3(pp, i1) * R[3 * i2 + j];
+        float ra = comp3(A, i1) * Q[3 * i2 + j] + comp3(A, i2) * Q[3 * i1 + j];
+        float rb = comp3(B, j1) * Q[3 * i + j2] + comp3(B, j2) * Q[3 * i + j1];
+        s = (fabsf(e) - (ra + rb)) * rsqrtf(l2);
+      }
       if (s > 0.f) return 0;
-      if (s > best * (1.0f / fudge) + 1e-6f) { best = s; code = 6 + 3 * i + j; flip = e < 0.f; nbest = ax; }
+      if (s > best * (1.0f / fudge) + 1e-6f) { best = s; code = 6 + 3 * i + j; flip = e < 0.f; }
     }
+  }
+  if (code >= 6) { int i = (code - 6) / 3, j = (code - 6) % 3; f3 ax = cross3(rcol(R1, i), rcol(R2, j)); nbest = ax * (1.0f / norm3(ax)); }
   f3 n = flip ? nbest * -1.0f : nbest;
   float depth = -best;
   if (code >= 6) {
@@ -155,6 +168,9 @@ FM_HD int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 B
   const float lim[2] = {comp3(Sr, r1), comp3(Sr, r2)};
   for (int c = 0; c < 2; ++c)
     for (int sg = -1; sg <= 1; sg += 2) {
+      bool any_out = false;                       // a side plane that cuts nothing leaves the polygon as it is (most do)
+      for (int k = 0; k < np; ++k) any_out = any_out || (lim[c] - sg * poly[k][c] < 0.f);
+      if (!any_out) continue;
       int nn = 0;
       for (int k = 0; k < np; ++k) {
         const float* a = poly[k]; const float* b = poly[(k + 1) % np];

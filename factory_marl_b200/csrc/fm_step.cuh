@@ -685,6 +685,14 @@ FM_HD void side_apply(const SideW& o, f3 n, f3 t1, f3 t2, float* cube, float* ar
   }
 }
 
+// warm start of contact c: forces of the previous solve for the same contact (geom pair + index); binary search on sorted keys
+template <int NA>
+FM_HD void warm_start_forces(EnvS<NA>& s, int c, int key) {
+  int lo = 0, hi = s.prev_n - 1, found = -1;
+  while (lo <= hi) { int mid = (lo + hi) >> 1; int pk = s.prev_key[mid]; if (pk == key) { found = mid; break; } if (pk < key) lo = mid + 1; else hi = mid - 1; }
+  for (int r = 0; r < 4; ++r) s.c_f[c][r] = found >= 0 ? s.prev_f[found][r] : 0.f;
+}
+
 template <int NA, int E>
 FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
@@ -695,16 +703,16 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
     int key = s.raw_key[ri];
     // rank = sorted position; arm-side slots are handed out in the same order (deterministic, independent of atomics)
     int rank = 0, slot_base = 0;
-    for (int k = 0; k < nraw; ++k) {
-      if (s.raw_key[k] < key) {
-        rank++;
-        int g = s.raw_g[k];
-        slot_base += (side_type(g & FM_SIDE_MASK) == FM_SIDE_ARM ? 1 : 0) + (side_type((g >> FM_SIDE_BITS) & FM_SIDE_MASK) == FM_SIDE_ARM ? 1 : 0);
-      }
-    }
+    for (int k = 0; k < nraw; ++k) rank += s.raw_key[k] < key ? 1 : 0;
     int c = rank;
     int g1 = key >> 13, g2 = (key >> 4) & 511;
     int rg = s.raw_g[ri];
+    if ((rg >> 30) & 1)     // only contacts of arm geoms need a slot for their arm-side Jacobian
+      for (int k = 0; k < nraw; ++k) {
+        int g = s.raw_g[k];
+        if (((g >> 30) & 1) && s.raw_key[k] < key)
+          slot_base += (side_type(g & FM_SIDE_MASK) == FM_SIDE_ARM ? 1 : 0) + (side_type((g >> FM_SIDE_BITS) & FM_SIDE_MASK) == FM_SIDE_ARM ? 1 : 0);
+      }
     int sd1 = rg & FM_SIDE_MASK, sd2 = (rg >> FM_SIDE_BITS) & FM_SIDE_MASK; bool armgeom = (rg >> 30) & 1;
     f3 p = mk3(s.raw_d[ri][0], s.raw_d[ri][1], s.raw_d[ri][2]), n = mk3(s.raw_d[ri][3], s.raw_d[ri][4], s.raw_d[ri][5]);
     float dist = s.raw_d[ri][6];
@@ -791,9 +799,7 @@ FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restr
     // warm start: forces of the previous solve for the same contact (geom pair + index); binary search on sorted keys.
     // (MuJoCo warm-starts the dual from qacc_warmstart as f = -jar/R; in fp32 that quotient is dominated by rounding.)
     s.c_key[c] = key;
-    int lo = 0, hi = s.prev_n - 1, found = -1;
-    while (lo <= hi) { int mid = (lo + hi) >> 1; int pk = s.prev_key[mid]; if (pk == key) { found = mid; break; } if (pk < key) lo = mid + 1; else hi = mid - 1; }
-    for (int r = 0; r < 4; ++r) s.c_f[c][r] = found >= 0 ? s.prev_f[found][r] : 0.f;
+    warm_start_forces(s, c, key);
   }
 }
 
@@ -1051,6 +1057,133 @@ FM_HD void ph_check(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   }
 }
 
+// Exact solve of an island that is ONE cube against static geoms / the belt (the common case: a cube landing on, tumbling on
+// or riding the belt).  The primal problem of MuJoCo's soft constraints has only the cube's 6 accelerations as unknowns:
+//   min_a 1/2 (a - a0)^T M (a - a0) + sum_rows s_r(J_r a - aref_r),  s_r(x) = x^2 / (2 R_r) for x < 0, else 0   [3P]
+// (M = diag(m, m, m, I, I, I): isotropic cube, angular part in the world frame; the belt dof is held at its lagged acceleration),
+// whose optimality condition is the fixed point of the dual PGS above with f_r = max(-x_r, 0) / R_r.  Active-set Newton:
+// rows with x < 0 at the current a form the set, (M + sum J^T J / R) a = M a0 + sum J^T aref / R is solved by a 6x6 Cholesky,
+// repeat until the set is stable (rows that still flip do so within `tol`).  Up to 8 contacts (32 rows, one bit each).
+// Returns false (forces stored, acc made consistent with them) if the set did not settle, and the caller sweeps.
+// one pass over the island's contacts at acceleration a: active set, forces f = max(-x, 0) / R (stored), belt projection;
+// ASSEMBLE adds the active rows to H (packed lower triangle) and g
+template <int NA, bool ASSEMBLE>
+FM_HD unsigned newton_cube_pass(EnvS<NA>& s, int c0, int c1, f3 xk, float ab, const float* a, unsigned act, float& chg, float* H, float* g) {
+  unsigned nact = 0; chg = 0.f;
+  const f3 al = mk3(a[0], a[1], a[2]), aa = mk3(a[3], a[4], a[5]);
+  for (int ci = c0; ci < c1; ++ci) {
+    const int c = s.isl_list[ci];
+    const int cs = s.c_side[c];
+    const int sd0 = cs & FM_SIDE_MASK, sd1 = (cs >> FM_SIDE_BITS) & FM_SIDE_MASK;
+    const bool cube0 = side_type(sd0) == FM_SIDE_CUBE;
+    const float sg = cube0 ? -1.f : 1.f;                                  // the cube is side 0 (-) or side 1 (+)
+    const bool belt = side_type(cube0 ? sd1 : sd0) == FM_SIDE_BELT;
+    const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+    const f3 rv = ld3(s.c_p[c]) - xk;
+    // base rows (normal, tangent 1, tangent 2) of the cube side: v = sg * (d ; r x d); belt side: the constant -sg * d.y * a_belt
+    const f3 dl[3] = {n * sg, t1 * sg, t2 * sg};
+    const f3 da[3] = {cross3(rv, dl[0]), cross3(rv, dl[1]), cross3(rv, dl[2])};
+    float ub[3], kb[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { kb[q] = belt ? -dl[q].y * ab : 0.f; ub[q] = dot3(dl[q], al) + dot3(da[q], aa) + kb[q]; }
+    const float mu = s.c_mu[c], D = 1.f / s.c_R[c];
+    float f[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+      const float aref = s.c_aref[c][r];
+      const float x = ub[0] + cf * ub[tq] - aref;
+      const bool on = x < 0.f;
+      const unsigned bit = 1u << (4 * (ci - c0) + r);
+      if (on != ((act & bit) != 0)) chg = fmaxf(chg, fabsf(x));
+      f[r] = on ? -D * x : 0.f;
+      if (on) nact |= bit;
+      if (ASSEMBLE && on) {
+        const f3 vl = dl[0] + dl[tq] * cf, va = da[0] + da[tq] * cf;
+        const float v[6] = {vl.x, vl.y, vl.z, va.x, va.y, va.z};
+        const float cst = kb[0] + cf * kb[tq] - aref;
+        int h = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float dv = D * v[i];
+          g[i] -= dv * cst;
+#pragma unroll
+          for (int j = 0; j <= i; ++j) H[h++] += dv * v[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s.c_f[c][r] = f[r];
+    float bs = 0.f;
+    if (belt) {   // belt-dof projection of this contact's force (other side: sign -sg)
+      const float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
+      bs = -(dl[0].y * Fn + dl[1].y * F1 + dl[2].y * F2);
+    }
+    c_belt(s, c) = bs;
+  }
+  return nact;
+}
+
+template <int NA>
+FM_HD bool island_newton_cube(EnvS<NA>& s, const FmDevModel& m, int k, int c0, int c1, float tol) {
+  float* acc = &s.acc[1 + 6 * k];
+  float a[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) a[q] = acc[q];
+  const float ab = s.acc[0];
+  const float invm = m.cube_invm[k], invI = m.cube_invI[k];
+  const float mass = 1.f / invm, In = 1.f / invI;
+  const f3 xk = ld3(s.cube_x[k]);
+  unsigned act = 0; bool ok = false;
+  for (int it = 0; it < 5 && !ok; ++it) {
+    FM_DBG(fm_dbg_sat[302]++;)
+    float H[21], g[6] = {0.f, 0.f, -mass * m.g, 0.f, 0.f, 0.f}, chg;
+#pragma unroll
+    for (int q = 0; q < 21; ++q) H[q] = 0.f;
+    H[0] = mass; H[2] = mass; H[5] = mass; H[9] = In; H[14] = In; H[20] = In;
+    act = newton_cube_pass<NA, true>(s, c0, c1, xk, ab, a, act, chg, H, g);     // active set at a, assembled
+    // 6x6 Cholesky solve H a = g (packed lower triangle, fully unrolled: registers)
+    float iv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      float d = H[tri(j, j)];
+#pragma unroll
+      for (int q = 0; q < j; ++q) d -= H[tri(j, q)] * H[tri(j, q)];
+      iv[j] = rsqrtf(fmaxf(d, 1e-30f));
+#pragma unroll
+      for (int i = j + 1; i < 6; ++i) {
+        float v = H[tri(i, j)];
+#pragma unroll
+        for (int q = 0; q < j; ++q) v -= H[tri(i, q)] * H[tri(j, q)];
+        H[tri(i, j)] = v * iv[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { float v = g[i]; for (int q = 0; q < i; ++q) v -= H[tri(i, q)] * a[q]; a[i] = v * iv[i]; }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) { float v = a[i]; for (int q = i + 1; q < 6; ++q) v -= H[tri(q, i)] * a[q]; a[i] = v * iv[i]; }
+    // verification at the new a (no assembly): stable set, or only rows within tol of the switching point flipped
+    unsigned nact = newton_cube_pass<NA, false>(s, c0, c1, xk, ab, a, act, chg, nullptr, nullptr);
+    if (nact == act || chg < tol) { ok = true; FM_DBG(fm_dbg_sat[311 + it]++;) }
+  }
+  if (!ok) {   // not settled (no line search here): back to the warm start, a = a0 + Minv J^T f, and the caller sweeps
+    f3 Fs = mk3(0, 0, 0), Ts = mk3(0, 0, 0);
+    for (int ci = c0; ci < c1; ++ci) {
+      const int c = s.isl_list[ci];
+      warm_start_forces(s, c, s.c_key[c]);
+      const float sg = side_type(s.c_side[c] & FM_SIDE_MASK) == FM_SIDE_CUBE ? -1.f : 1.f;
+      const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+      const float* f = s.c_f[c]; const float mu = s.c_mu[c];
+      const f3 F = (n * (f[0] + f[1] + f[2] + f[3]) + t1 * (mu * (f[0] - f[1])) + t2 * (mu * (f[2] - f[3]))) * sg;
+      Fs = Fs + F; Ts = Ts + cross3(ld3(s.c_p[c]) - xk, F);
+    }
+    a[0] = Fs.x * invm; a[1] = Fs.y * invm; a[2] = Fs.z * invm - m.g; a[3] = Ts.x * invI; a[4] = Ts.y * invI; a[5] = Ts.z * invI;
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) acc[q] = a[q];
+  return ok;
+}
+
 // phase: projected Gauss-Seidel, one lane per constraint island.  Islands whose warm start already satisfies the stopping
 // criterion (every row's update below tol, the steady state of resting contacts) are left as they are.
 template <int NA, int E>
@@ -1069,7 +1202,16 @@ FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
     for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, c_res(s, s.isl_list[ci]));
     FM_DBG(fm_dbg_islands++;)
     FM_DBG(int dbg_kind = has_arm ? (c1 > c0 ? 2 : 1) : 0; int dbg_sw = 0; fm_dbg_cnt[4 + 4 * dbg_kind]++; fm_dbg_cnt[7 + 4 * dbg_kind] += c1 - c0;)
-    if (maxd >= tol) {
+    bool solved = false;
+    if (maxd >= tol && !has_arm && node < FM_NCUBE && c1 - c0 <= 8) {
+      bool alone = true;                                     // no other node was merged into this island
+      if (s.need_union) for (int i = 0; i < NN; ++i) alone = alone && (i == node || s.isl_root[i] != node);
+#ifndef FM_NO_NEWTON
+      if (alone) solved = island_newton_cube(s, m, node, c0, c1, tol);
+#endif
+      FM_DBG(if (alone) { fm_dbg_sat[300]++; fm_dbg_sat[301] += solved; })
+    }
+    if (maxd >= tol && !solved) {
       // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
       // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236);
       // a lone arm with only its plate equality row is solved exactly by one visit

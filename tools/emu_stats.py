@@ -18,9 +18,11 @@ lib = emu_lib()
 lib.fm_emu_counters2.argtypes = [C.c_void_p]
 def cnt():
     o = (C.c_longlong * 32)(); lib.fm_emu_counters2(o); return np.array(list(o), dtype=np.int64)
-base = None
+base = None; sbase = None
+def satc():
+    o = (C.c_longlong * 512)(); lib.fm_emu_sat.argtypes = [C.c_void_p]; lib.fm_emu_sat(o); return np.array(list(o))
 for t in range(steps):
-    if t == skip: base = cnt()
+    if t == skip: base = cnt(); sbase = satc()
     a = np.clip(rng.standard_normal((n, 16)), -1, 1).astype(np.float32)
     core.env_step(a)
 c = cnt() - base
@@ -32,5 +34,7 @@ for k, nm in enumerate(["cube-only", "arm-only", "arm+contacts"]):
 print("cube-only sweep histogram", (c[16:26] / max(c[16:26].sum(), 1)).round(3))
 print("box-box per substep: fast path %.3f, far-sphere reject %.3f, general SAT %.3f (with an arm geom %.3f)" % (c[27] / ss, c[28] / ss, c[29] / ss, c[30] / ss))
 o = (C.c_longlong * 512)(); lib.fm_emu_sat.argtypes = [C.c_void_p]; lib.fm_emu_sat(o)
-sat = np.array(list(o)); names = model.assemble(2)["geom_names"] if hasattr(model, "assemble") else None
+sat = np.array(list(o)) - sbase; names = model.assemble(2)["geom_names"] if hasattr(model, "assemble") else None
 print("general SAT by geom1 id (whole run):", {int(k): int(sat[k]) for k in np.nonzero(sat)[0]})
+print("single-cube Newton: calls/substep %.3f, settled %.4f, iterations/call %.2f" % (sat[300] / ss, sat[301] / max(sat[300], 1), sat[302] / max(sat[300], 1)))
+print("Newton iterations-to-settle histogram (1..5):", (sat[311:316] / max(sat[311:316].sum(), 1)).round(3))
