@@ -138,7 +138,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout when the first communicator is created: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev); dist.all_reduce(warm); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     n = args.envs
     K, W = args.steps, max(args.warmup, 3)
     env = FactoryVecEnv(ENV_CLASS, num_envs=n, num_arms=2, seeds=list(range(42 + rank * n, 42 + (rank + 1) * n)),

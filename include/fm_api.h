@@ -25,7 +25,10 @@ enum { FM_FACTORY_MANIPULATION_ENV = 0, FM_SINGLE_FULL_RL = 1, FM_SINGLE_DELTA =
  * (src/environments.py:252-259) + solver knobs of this implementation. */
 typedef struct fm_config {
   int32_t n_envs, n_arms, env_class, auto_reset;
-  int32_t pgs_outer, pgs_inner, envs_per_block, reserved;   /* reserved: 1 = keep hidden cubes live (strict mode), 0 = sleep them at rest */
+  /* pgs_inner: sweep cap of the PGS islands (0 = 4), pgs_tol: stopping criterion in m/s^2 (0 = 1e-3), pgs_outer: unused.
+   * envs_per_block: block shape of the step kernel: 0 = by batch size, 1 | 4 = small batches / tests, 14 (two arms) | 7 (four
+   * arms) = one block per SM (default from 2048 envs).  reserved: 1 = keep hidden cubes live (strict mode), 0 = sleep them. */
+  int32_t pgs_outer, pgs_inner, envs_per_block, reserved;
   float pgs_tol, reserved_f;
   double initial_conveyor_speed, conveyor_acceleration, pt_time, force_contact_threshold, control_frequency,
       spawn_freq, spawn_freq_increase;
