@@ -244,7 +244,7 @@ def run_ours(args):
         samples = world * n * args.ppo_steps
         ppo_info = {"samples_per_s": samples / (float(tp[0]) * 1e-3), "rollout_ms": float(tp[1]), "update_ms": float(tp[0] - tp[1]),
                     "samples": samples, "n_steps": args.ppo_steps, "batch_size": algo.batch_size, "n_epochs": 10,
-                    "optimizer_steps": info["n_updates"], "approx_kl": info["approx_kl"], "clip_fraction": info["clip_fraction"],
+                    "optimizer_steps": info["n_updates"], "cuda_graph": info.get("cuda_graph"), "approx_kl": info["approx_kl"], "clip_fraction": info["clip_fraction"],
                     "grad_allreduce": "nccl" if world > 1 else "none"}
     if rank == 0:
         hbm_peak, peak_kind, sm_max = peaks()

@@ -319,20 +319,28 @@ __global__ void colsum_kernel(const bf16* __restrict__ d, int n, int ld, int col
   atomicAdd(&out[c], s);
 }
 
-// global-norm clip + Adam (torch.optim.Adam semantics, eps 1e-5 from policy.optimizer.pth) + refresh of the bf16 copy; single CTA
-__global__ void __launch_bounds__(1024) adam_kernel(float* __restrict__ p, bf16* __restrict__ pb, float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float max_norm,
-                                                    float grad_scale, int step, float* __restrict__ stats) {
-  __shared__ float red[1024];
+// global-norm clip + Adam (torch.optim.Adam semantics, eps 1e-5 from policy.optimizer.pth) + refresh of the bf16 copy.
+// Two launches over the ~1e5 parameters: squared-norm partial sums into norm2[0] (zeroed by a memset node before), then the update.
+#define FM_ADAM_BLOCKS 64
+__global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict__ g, int n, float grad_scale, float* __restrict__ norm2) {
+  __shared__ float red[256];
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) { float x = g[i] * grad_scale; s += x * x; }
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) { float x = g[i] * grad_scale; s += x * x; }
   red[threadIdx.x] = s;
   __syncthreads();
-  for (int k = 512; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
-  float norm = sqrtf(red[0]);
+  for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) atomicAdd(norm2, red[0]);
+}
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, bf16* __restrict__ pb, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float max_norm,
+                                                   float grad_scale, int step, const float* __restrict__ norm2, float* __restrict__ stats) {
+  float norm = sqrtf(norm2[0]);
   float cs = fminf(1.f, max_norm / (norm + 1e-6f)) * grad_scale;   // torch.nn.utils.clip_grad_norm_
-  float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  for (int i = threadIdx.x; i < n; i += 1024) {
+  // step <= 0: the step count lives on the device in stats[7] (a captured CUDA graph replays this launch with fixed arguments);
+  // it is advanced by adam_count_kernel after this launch
+  const int st = step > 0 ? step : (int)stats[7] + 1;
+  float bc1 = 1.f - powf(b1, (float)st), bc2 = 1.f - powf(b2, (float)st);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     float x = g[i] * cs;
     float mi = b1 * m[i] + (1.f - b1) * x, vi = b2 * v[i] + (1.f - b2) * x * x;
     m[i] = mi; v[i] = vi;
@@ -341,7 +349,10 @@ __global__ void __launch_bounds__(1024) adam_kernel(float* __restrict__ p, bf16*
     p[i] = np_; pb[i] = __float2bfloat16(np_);
     g[i] = 0.f;
   }
-  if (threadIdx.x == 0 && stats) stats[5] = norm;
+}
+__global__ void adam_count_kernel(int step, const float* __restrict__ norm2, float* __restrict__ stats) {
+  stats[5] = sqrtf(norm2[0]);
+  if (step <= 0) stats[7] = stats[7] + 1.f;
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,7 +371,7 @@ static int mlp_forward(const fm_ppo_net* net, const fm_ppo_ws* ws, int which, in
 static int mlp_backward(const fm_ppo_net* net, const fm_ppo_ws* ws, int which, int n, cudaStream_t s) {
   const bf16* P = net->params_bf16; float* G = net->grads;
   int Dp = net->obs_pad, Op = which == 0 ? net->out_pad : 16;
-  int sk = n >= 4096 ? 16 : (n >= 1024 ? 8 : (n >= 256 ? 4 : 1));
+  int sk = n >= 4096 ? 64 : (n >= 1024 ? 16 : (n >= 256 ? 4 : 1));   // split-K of the weight-gradient GEMMs (K = rows): >= 148 CTAs
   dim3 cb(64);
   colsum_kernel<<<dim3((Op + 63) / 64, (n + 255) / 256), cb, 0, s>>>(ws->dout[which], n, Op, Op, G + net->b3[which]);
   // dW3[128,Op] += H2^T dOUT ; dH2 = (dOUT W3^T) * (1 - H2^2)
@@ -438,11 +449,18 @@ int fm_ppo_update(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, 
 }
 
 /* clip_grad_norm_(max_grad_norm) + Adam step (lr 3e-4, eps 1e-5, runs/r666unuv.json:51-52); grads *= grad_scale first
- * (1/world after the NCCL sum all-reduce); zeroes the gradients and refreshes the bf16 parameter copy. */
+ * (1/world after the NCCL sum all-reduce); zeroes the gradients and refreshes the bf16 parameter copy.  step = Adam's t
+ * (1-based); step <= 0 takes t from stats[7] on the device and increments it there (for CUDA-graph replay). */
 int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, int step,
                  float* stats, void* stream) {
-  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(net->params, net->params_bf16, net->grads, net->adam_m, net->adam_v, net->n_params, lr, beta1,
-                                                    beta2, eps, max_grad_norm, grad_scale, step, stats);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!stats) { g_ppo_err = "fm_adam_step: stats (8 floats on the device) is required"; return 1; }
+  float* norm2 = stats + 6;
+  PPO_CUDA(cudaMemsetAsync(norm2, 0, sizeof(float), s));
+  grad_norm_kernel<<<FM_ADAM_BLOCKS, 256, 0, s>>>(net->grads, net->n_params, grad_scale, norm2);
+  adam_kernel<<<FM_ADAM_BLOCKS, 256, 0, s>>>(net->params, net->params_bf16, net->grads, net->adam_m, net->adam_v, net->n_params, lr, beta1, beta2, eps,
+                                             max_grad_norm, grad_scale, step, norm2, stats);
+  adam_count_kernel<<<1, 1, 0, s>>>(step, norm2, stats);
   PPO_CUDA(cudaGetLastError());
   return 0;
 }

@@ -211,7 +211,7 @@ class PPO:
     summed with one NCCL all-reduce per optimiser step and divided by the world size (advantage normalisation stays rank-local)."""
 
     def __init__(self, env, n_steps=32, batch_size=8192, n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, vf_coef=0.5,
-                 ent_coef=0.0, learning_rate=3e-4, max_grad_norm=0.5, adam_eps=1e-5, normalize_advantage=True, seed=0):
+                 ent_coef=0.0, learning_rate=3e-4, max_grad_norm=0.5, adam_eps=1e-5, normalize_advantage=True, seed=0, use_graph=True):
         self.env, self.dev = env, env.device
         c = env.core
         N, D, A = c.num_envs, c.obs_dim, c.act_dim
@@ -233,6 +233,7 @@ class PPO:
         self.num_timesteps = 0
         self.ep_returns, self.ep_lengths, self.ep_scores = [], [], []
         self.launches = 0
+        self.use_graph, self._graphs, self._idx = use_graph, None, None
 
     def collect_rollouts(self):
         env, pol = self.env, self.pol
@@ -256,31 +257,71 @@ class PPO:
         # Monitor / ep_score_history analogue (learning.py:53-72): read once per rollout, not once per step
         pass
 
-    def train(self):
+    def _minibatch_eager(self, idx_ptr, step):
+        pol = self.pol
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        total = self.n_steps * self.env.num_envs
+        obs = self.b_obs.view(total, -1); act = self.b_act.view(total, -1)
+        pol._chk(self.lib.fm_ppo_update(C.byref(pol.net), C.byref(pol._ws), obs.data_ptr(), act.data_ptr(), self.b_logp.data_ptr(),
+                                        self.b_adv.data_ptr(), self.b_ret.data_ptr(), idx_ptr, self.batch_size, self.clip, self.vf, self.ent,
+                                        int(self.norm_adv), self.stats.data_ptr(), s))
+        if self.world > 1:      # the only inter-GPU exchange of the path: one sum all-reduce of the flat gradient (NCCL / NVLink)
+            torch.distributed.all_reduce(pol.grads, op=torch.distributed.ReduceOp.SUM)
+        pol._chk(self.lib.fm_adam_step(C.byref(pol.net), self.lr, 0.9, 0.999, self.eps, self.max_norm, 1.0 / self.world, step,
+                                       self.stats.data_ptr(), s))
+
+    def _capture_graphs(self):
+        """One optimiser step = 33 short launches (launch-bound: K <= 320, N = 128 GEMMs): captured once into CUDA graphs and
+        replayed with a static minibatch-index buffer; Adam's step count lives on the device (stats[7]).  With several ranks the
+        NCCL all-reduce stays between two graphs (update | all-reduce | Adam)."""
         pol = self.pol
         total = self.n_steps * self.env.num_envs
         obs = self.b_obs.view(total, -1); act = self.b_act.view(total, -1)
-        logp, adv, ret = self.b_logp.view(-1), self.b_adv.view(-1), self.b_ret.view(-1)
-        s = lambda: torch.cuda.current_stream(self.dev).cuda_stream
+        self._idx = torch.zeros(self.batch_size, dtype=torch.int32, device=self.dev)
+        g_upd, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        cs = lambda: torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.graph(g_upd):
+            pol._chk(self.lib.fm_ppo_update(C.byref(pol.net), C.byref(pol._ws), obs.data_ptr(), act.data_ptr(), self.b_logp.data_ptr(),
+                                            self.b_adv.data_ptr(), self.b_ret.data_ptr(), self._idx.data_ptr(), self.batch_size, self.clip,
+                                            self.vf, self.ent, int(self.norm_adv), self.stats.data_ptr(), cs()))
+            if self.world == 1:
+                pol._chk(self.lib.fm_adam_step(C.byref(pol.net), self.lr, 0.9, 0.999, self.eps, self.max_norm, 1.0, 0, self.stats.data_ptr(), cs()))
+        if self.world > 1:
+            with torch.cuda.graph(g_adam):
+                pol._chk(self.lib.fm_adam_step(C.byref(pol.net), self.lr, 0.9, 0.999, self.eps, self.max_norm, 1.0 / self.world, 0,
+                                               self.stats.data_ptr(), cs()))
+        self._graphs = (g_upd, g_adam)
+
+    def train(self):
+        pol = self.pol
+        total = self.n_steps * self.env.num_envs
         nb = total // self.batch_size
-        self.stats.zero_()
+        self.stats[:7].zero_()
         n_updates = 0
+        # the first call runs launch by launch (it also sets the kernels' attributes); the graphs are captured after it
+        use_graph = self.use_graph and self._graphs is not None
+        if use_graph:
+            self.stats[7:8].fill_(float(pol.adam_step))
         for ep in range(self.n_epochs):
             perm = torch.randperm(total, device=self.dev, generator=self.gen, dtype=torch.int64).to(torch.int32)
             for b in range(nb):
-                idx = perm[b * self.batch_size:(b + 1) * self.batch_size].contiguous()
-                pol._chk(self.lib.fm_ppo_update(C.byref(pol.net), C.byref(pol._ws), obs.data_ptr(), act.data_ptr(), logp.data_ptr(),
-                                                adv.data_ptr(), ret.data_ptr(), idx.data_ptr(), self.batch_size, self.clip, self.vf, self.ent,
-                                                int(self.norm_adv), self.stats.data_ptr(), s()))
-                if self.world > 1:      # the only inter-GPU exchange of the path: one sum all-reduce of the flat gradient (NCCL / NVLink)
-                    torch.distributed.all_reduce(pol.grads, op=torch.distributed.ReduceOp.SUM)
                 pol.adam_step += 1
-                pol._chk(self.lib.fm_adam_step(C.byref(pol.net), self.lr, 0.9, 0.999, self.eps, self.max_norm, 1.0 / self.world, pol.adam_step,
-                                               self.stats.data_ptr(), s()))
+                if use_graph:
+                    self._idx.copy_(perm[b * self.batch_size:(b + 1) * self.batch_size])
+                    self._graphs[0].replay()
+                    if self.world > 1:
+                        torch.distributed.all_reduce(pol.grads, op=torch.distributed.ReduceOp.SUM)
+                        self._graphs[1].replay()
+                else:
+                    idx = perm[b * self.batch_size:(b + 1) * self.batch_size].contiguous()
+                    self._minibatch_eager(idx.data_ptr(), pol.adam_step)
                 n_updates += 1
                 self.launches += 33
+        if self.use_graph and self._graphs is None:
+            self._capture_graphs()
         return {"n_updates": n_updates, "policy_loss": float(self.stats[0]) / max(n_updates, 1), "value_loss": float(self.stats[1]) / max(n_updates, 1),
-                "approx_kl": float(self.stats[2]) / max(n_updates, 1), "clip_fraction": float(self.stats[3]) / max(n_updates, 1)}
+                "approx_kl": float(self.stats[2]) / max(n_updates, 1), "clip_fraction": float(self.stats[3]) / max(n_updates, 1),
+                "cuda_graph": bool(use_graph)}
 
     def learn(self, total_timesteps: int, log=None):
         it = 0

@@ -98,7 +98,9 @@ int fm_gae(const float* rewards, const float* values, const uint8_t* dones, cons
 int fm_ppo_update(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, const float* actions, const float* old_logp,
                   const float* adv, const float* ret, const int32_t* idx, int n, float clip_range, float vf_coef, float ent_coef,
                   int normalize_advantage, float* stats, void* stream);
-/* clip_grad_norm_ + Adam on the flat parameter buffer (after the NCCL all-reduce of net->grads; grad_scale = 1/world) */
+/* clip_grad_norm_ + Adam on the flat parameter buffer (after the NCCL all-reduce of net->grads; grad_scale = 1/world).
+ * stats: 8 floats on the device (required): [5] <- gradient norm, [6] scratch, [7] Adam's step count when step <= 0 (the
+ * launch sequence then has no host-side argument that changes between steps, so it can be replayed from a CUDA graph). */
 int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, int step,
                  float* stats, void* stream);
 int fm_ppo_sync_bf16(const fm_ppo_net* net, void* stream);

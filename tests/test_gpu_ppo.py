@@ -129,14 +129,16 @@ def test_adam_step_matches_torch():
     ref = p0.clone().requires_grad_(True)
     opt = torch.optim.Adam([ref], lr=3e-4, eps=1e-5)
     g = torch.Generator(device="cuda").manual_seed(2)
+    stats = torch.zeros(8, device="cuda")
     for step in range(1, 4):
         grad = torch.randn(pol.n_params, device="cuda", generator=g) * 0.01
         pol.grads.copy_(grad * 2.0)                     # as if summed over 2 ranks
         ref.grad = grad.clone()
         torch.nn.utils.clip_grad_norm_([ref], 0.5)
         opt.step()
-        assert pol.lib.fm_adam_step(C.byref(pol.net), 3e-4, 0.9, 0.999, 1e-5, 0.5, 0.5, step, None, None) == 0
+        assert pol.lib.fm_adam_step(C.byref(pol.net), 3e-4, 0.9, 0.999, 1e-5, 0.5, 0.5, step, stats.data_ptr(), None) == 0
         torch.cuda.synchronize()
+        assert abs(float(stats[5]) - float(grad.norm())) < 1e-4 * float(grad.norm())     # global gradient norm before clipping
         assert torch.allclose(pol.params, ref.detach(), atol=2e-6, rtol=1e-5)
         assert float(pol.grads.abs().max()) == 0.0
     assert torch.allclose(pol.params_bf16.float(), pol.params, atol=1e-2, rtol=1e-2)
@@ -179,3 +181,25 @@ def test_tcgen05_mlp_matches_mma_sync_and_fp32(obs_dim, act_dim, discrete):
     assert torch.allclose(out_tc5[:, :n_out], pi, atol=2e-2, rtol=2e-2), float((out_tc5[:, :n_out] - pi).abs().max())
     assert torch.allclose(val_tc5, v, atol=2e-2, rtol=2e-2)
     assert torch.allclose(out_tc5, out_mma, atol=1e-2, rtol=1e-2) and torch.allclose(val_tc5, val_mma, atol=1e-2, rtol=1e-2)
+
+
+def test_graph_replayed_optimizer_steps_match_launch_by_launch():
+    """PPO.train replays one captured CUDA graph per optimiser step from the second call on (Adam's step count on the device);
+    same rollouts, same minibatch permutations -> same parameters as the launch-by-launch path (split-K atomics: to 1e-5)."""
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    from factory_marl_b200.ppo import PPO
+    res = []
+    for use_graph in (False, True):
+        env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=64, num_arms=2, seed=3, gripper_to_closest_cube_reward_factor=0.2,
+                            closest_cube_to_bucket_reward_factor=0.4, base_reward=0.4)
+        algo = PPO(env, n_steps=4, batch_size=128, n_epochs=2, seed=1, use_graph=use_graph)
+        infos = []
+        for _ in range(3):
+            algo.collect_rollouts(); infos.append(algo.train())
+        assert [i["cuda_graph"] for i in infos] == [False, use_graph, use_graph]
+        res.append((algo.pol.params.clone(), algo.pol.adam_step, infos[-1]))
+        env.close()
+    (p0, s0, i0), (p1, s1, i1) = res
+    assert s0 == s1 == 3 * 2 * 2
+    assert torch.isfinite(p1).all() and float((p0 - p1).abs().max()) < 1e-4, float((p0 - p1).abs().max())
+    assert abs(i0["approx_kl"] - i1["approx_kl"]) < 1e-4
