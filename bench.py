@@ -30,7 +30,8 @@ N_ENVS_PER_GPU = 4096
 METRIC = "batched TaskEnv env-steps/sec"
 UNIT = "env-steps/s"
 # algorithmic work per env-step (DESIGN.md "Measurement"): state in+out + action + obs + scalars, fp32 flop hand count
-FLOP_PER_ENV_STEP = 2.1e7
+FLOP_PER_ENV_STEP = 2.1e7            # SURVEY.md 8d hand count of the path as MuJoCo runs it (25 solver iterations over ~170 rows)
+FLOP_PER_ENV_STEP_EXECUTED = 4.76e6   # fp32 flop this kernel executes per env-step in the bench workload: ncu fadd + fmul + 2 ffma (profiles/r1m)
 # dram__bytes_read.sum + dram__bytes_write.sum of fm_step_kernel per env, from the ncu --set full capture profiles/r1e_step_kernel_ncu_raw.csv
 # (6.13 MB per launch of 1184 envs); the launch at bench size was not captured separately
 DRAM_BYTES_PER_ENV_NCU = 6.13e6 / 1184
@@ -262,6 +263,10 @@ def run_ours(args):
                              "note": "the step kernel is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d); see roofline_fp32"},
                 "roofline_fp32": {"achieved": FLOP_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                                   "frac": FLOP_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e12 / fp32_peak, "flop_per_env_step": FLOP_PER_ENV_STEP,
+                                  "flop_per_env_step_executed": FLOP_PER_ENV_STEP_EXECUTED,
+                                  "achieved_executed": FLOP_PER_ENV_STEP_EXECUTED * n / (kern_ms * 1e-3) / 1e12,
+                                  "frac_executed": FLOP_PER_ENV_STEP_EXECUTED * n / (kern_ms * 1e-3) / 1e12 / fp32_peak,
+                                  "note": "achieved = SURVEY's algorithmic hand count / kernel time; *_executed = flop the kernel really issues (ncu): warm-started islands that are already converged, sleeping cubes and the 6x6 Newton solve do 4.4x less arithmetic than the hand count assumes",
                                   "peak_source": "148 SM x 128 lanes x 2 x max SM clock"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": sampler.result()}

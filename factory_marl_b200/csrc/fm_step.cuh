@@ -76,7 +76,7 @@ struct EnvS {
   int cube_sleep[FM_NCUBE];
   float cube_R[FM_NCUBE][9], cube_x[FM_NCUBE][3], cube_vw[FM_NCUBE][6];   // cube_vw: (v, R*omega_local)
   float body_x[NA][FM_NARMBODY][3], body_R[NA][FM_NARMBODY][9];
-  alignas(16) float bnd[FM_NCUBE + NA * FM_NARMBODY][4];   // bounding spheres (x, y, z, r) of the cube / arm-body clusters
+  alignas(8) float bnd[FM_NCUBE + NA * FM_NARMBODY][4];   // bounding spheres (x, y, z, r) of the cube / arm-body clusters
   float M[NA][45], Minv[NA][81], Li[NA][45], Lc[NA][45];
   float bias[NA][9], chol_d[NA][2][9];      // chol_d: diagonal of the Cholesky factors of M (0) and M - hD (1)
   // ---- acceleration stage
@@ -122,7 +122,8 @@ struct EnvS {
   int prev_arow_n[NA], prev_arow_code[NA][FM_AROW];
   float prev_arow_f[NA][FM_AROW];
   int c_key[FM_MAXCON];
-  int pad_[FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 4 (mod 32): envs of one block start on different shared-memory banks
+  int pad_[FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 2 (mod 32): the envs of a block start on different (even) shared-memory banks,
+                           // and the next item of an odd-stride array falls on the odd ones
 };
 
 // flags
@@ -448,7 +449,7 @@ FM_HD void cluster_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx
   }
 }
 
-struct alignas(16) bnd4 { float x, y, z, r; };
+struct alignas(8) bnd4 { float x, y, z, r; };   // two 64-bit loads: the env stride is 2 (mod 32) words, not a multiple of 4
 template <int NA, int E>
 FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
