@@ -39,8 +39,12 @@ FM_HD void fm_arm_kinematics(Run& run, EnvS<NA>* S, const FmDevModel& m, int T) 
   run([&](int tid) { ph_arm_plates<NA, E>(S, tid, T); });
 }
 
-template <int NA, int E, class Run>
-FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class, int T, int sleep_hidden) {
+// warps of the factorisation group / of the narrow-phase group when a block of TW warps splits (see fm_derive)
+FM_HDM constexpr int fm_split_a(int TW) { return TW >= 12 ? 8 : (TW >= 7 ? 5 : (TW >= 4 ? 3 : TW)); }
+
+template <int NA, int E, int TW, class Run>
+FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class, int sleep_hidden) {
+  const int T = 32 * TW;
   run([&](int tid) { ph_clear<NA, E>(S, tid, T); ph_cube_derive<NA, E>(S, m, tid, T, sleep_hidden); ph_arm_local<NA, E>(S, m, tid, T); });
   run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 1, true); });
   run([&](int tid) { ph_arm_scan<NA, E>(S, tid, T, 2, false); });
@@ -50,16 +54,25 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
   run([&](int tid) { ph_arm_body<NA, E>(S, m, tid, T); });
   run([&](int tid) { ph_arm_bwd<NA, E>(S, tid, T); ph_broad<NA, E>(S, m, cpairs, tid, T); });
   run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 0>(S, tid, T); ph_narrow<NA, E>(S, m, cpairs, tid, T); });   // raw contacts reuse the arm scratch
-  run([&](int tid) { ph_arm_chol_col<NA, E, 1>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 2>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 3>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 4>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 5>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 6>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 7>(S, tid, T); });
-  run([&](int tid) { ph_arm_chol_col<NA, E, 8>(S, tid, T); });
-  run([&](int tid) { ph_arm_minv<NA, E>(S, tid, T); });
+  // Two independent chains run side by side on disjoint warps: the ten intervals of the two 9x9 Cholesky factorisations and
+  // the explicit inverse (barrier among their warps only), and the narrow phase, whose longest item (a general box-box SAT,
+  // ~1.5 k dependent instructions on one lane) would otherwise hold every warp of the block at the next barrier.
+  // The raw contacts reuse the arm scratch, which is dead after ph_arm_M.
+  constexpr int WA = fm_split_a(TW), WB = TW - WA;
+  run.template split<WA, WB>(
+      [&](auto& sub, int TA) {
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 0>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 1>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 2>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 3>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 4>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 5>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 6>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 7>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_chol_col<NA, E, 8>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_minv<NA, E>(S, tid, TA); });
+      },
+      [&](int tid, int TB) { ph_narrow<NA, E>(S, m, cpairs, tid, TB); });
   run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T); ph_arm_rows<NA, E>(S, m, tid, T); });
 }
 
@@ -116,13 +129,13 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
   else run([&](int tid) {   // debug: ctrl_target is used as is (no filter): ctrl := ctrl_target
     for (int w = tid; w < EnvS<NA>::NU * E; w += T) S[w % E].ctrl[w / E] = S[w % E].ctrl_target[w / E];
   });
-  fm_derive<NA, E>(run, S, m, cpairs, geom_class, T, cfg.sleep_hidden);
+  fm_derive<NA, E, TW>(run, S, m, cpairs, geom_class, cfg.sleep_hidden);
   run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
   const double hd = cfg.dt / cfg.frame_skip;
   const float alpha = (float)(hd / (hd + cfg.pt_time));   // base_env.py:209-211
   const int nsub = ar.mode == 0 ? cfg.frame_skip : ar.n_substeps;
   for (int t = 0; t < nsub; ++t) {
-    if (t > 0) fm_derive<NA, E>(run, S, m, cpairs, geom_class, T, cfg.sleep_hidden);
+    if (t > 0) fm_derive<NA, E, TW>(run, S, m, cpairs, geom_class, cfg.sleep_hidden);
     run([&](int tid) { ph_island_union<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, alpha); });
     run([&](int tid) { ph_island_lists<NA, E>(S, tid, T); ph_smooth<NA, E>(S, m, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
