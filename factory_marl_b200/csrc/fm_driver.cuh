@@ -53,14 +53,22 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
   run([&](int tid) { ph_arm_vel<NA, E>(S, m, tid, T); });
   run([&](int tid) { ph_arm_body<NA, E>(S, m, tid, T); });
   run([&](int tid) { ph_arm_bwd<NA, E>(S, tid, T); ph_broad<NA, E>(S, m, cpairs, tid, T); });
-  run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); });
-  // Two independent chains run side by side on disjoint warps: the ten intervals of the two 9x9 Cholesky factorisations and
-  // the explicit inverse (barrier among their warps only), and the narrow phase, whose longest item (a general box-box SAT,
-  // ~1.5 k dependent instructions on one lane) would otherwise hold every warp of the block at the next barrier.
-  // The raw contacts reuse the arm scratch, which is dead after ph_arm_M.
+  // Two independent chains run side by side on disjoint warp groups, each with its own barrier:
+  //   A: mass matrix, the ten intervals of the two 9x9 Cholesky factorisations and the explicit inverse;
+  //   B: narrow phase, whose longest item (a general box-box SAT, ~1.5 k dependent instructions on one lane) would otherwise
+  //      hold every warp of the block at the next barrier.
+  // The raw contacts reuse arm scratch that is dead after ph_arm_bwd.  Measured (4096 envs, 10 steps): no split 277 k,
+  // {chol, minv} | narrow 293 k, {M, chol, minv} | narrow 300 k env-steps/s; also moving the set-up of the arm-free contacts
+  // into B (FM_SPLIT_MODE 3) needs a second copy of that large phase and loses 9 % again.
   constexpr int WA = fm_split_a(TW), WB = TW - WA;
+#ifndef FM_SPLIT_MODE
+#define FM_SPLIT_MODE 1
+#endif
+  constexpr bool M_IN_A = (FM_SPLIT_MODE & 1) != 0, SETUP_IN_B = (FM_SPLIT_MODE & 2) != 0;
+  if (!M_IN_A) run([&](int tid) { ph_arm_M<NA, E>(S, m, tid, T); });
   run.template split<WA, WB>(
       [&](auto& sub, int TA) {
+        if (M_IN_A) sub([&](int tid) { ph_arm_M<NA, E>(S, m, tid, TA); });
         sub([&](int tid) { ph_arm_chol_col<NA, E, 0>(S, tid, TA); });
         sub([&](int tid) { ph_arm_chol_col<NA, E, 1>(S, tid, TA); });
         sub([&](int tid) { ph_arm_chol_col<NA, E, 2>(S, tid, TA); });
@@ -72,8 +80,11 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
         sub([&](int tid) { ph_arm_chol_col<NA, E, 8>(S, tid, TA); });
         sub([&](int tid) { ph_arm_minv<NA, E>(S, tid, TA); });
       },
-      [&](int tid, int TB) { ph_narrow<NA, E>(S, m, cpairs, tid, TB); });
-  run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T); ph_arm_rows<NA, E>(S, m, tid, T); });
+      [&](auto& sub, int TB) {
+        sub([&](int tid) { ph_narrow<NA, E>(S, m, cpairs, tid, TB); });
+        if (SETUP_IN_B) sub([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, TB, 1); });
+      });
+  run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T, SETUP_IN_B ? 2 : 0); ph_arm_rows<NA, E>(S, m, tid, T); });
 }
 
 template <int NA, int E>

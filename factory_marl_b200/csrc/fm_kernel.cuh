@@ -25,21 +25,23 @@ cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t
 
 #ifdef FM_KERNEL_IMPL
 
-// barrier among the first WA warps of the block only (named barrier 1; barrier 0 is __syncthreads)
-template <int WA>
+// barrier among W consecutive warps of the block, starting at warp BASE (named barrier ID; barrier 0 is __syncthreads)
+template <int ID, int BASE, int W>
 struct DevGroupRun {
-  template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); asm volatile("bar.sync 1, %0;" ::"n"(32 * WA) : "memory"); }
+  template <class F> __device__ __forceinline__ void operator()(F f) {
+    f((int)threadIdx.x - 32 * BASE);
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(32 * W) : "memory");
+  }
 };
 struct DevRun {
   template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); __syncthreads(); }
-  // warps [0, WA) run the intervals of progA, warps [WA, WA + WB) run fB meanwhile; the whole block joins at the end
-  template <int WA, int WB, class PA, class FB> __device__ __forceinline__ void split(PA progA, FB fB) {
+  // warps [0, WA) run the intervals of progA, warps [WA, WA + WB) those of progB meanwhile; the whole block joins at the end
+  template <int WA, int WB, class PA, class PB> __device__ __forceinline__ void split(PA progA, PB progB) {
     if constexpr (WB == 0) {
-      progA(*this, 32 * WA);
-      fB((int)threadIdx.x, 32 * WA); __syncthreads();
+      progA(*this, 32 * WA); progB(*this, 32 * WA);
     } else {
-      if (threadIdx.x < 32 * WA) { DevGroupRun<WA> sub; progA(sub, 32 * WA); }
-      else fB((int)threadIdx.x - 32 * WA, 32 * WB);
+      if (threadIdx.x < 32 * WA) { DevGroupRun<1, 0, WA> sub; progA(sub, 32 * WA); }
+      else { DevGroupRun<2, WA, WB> sub; progB(sub, 32 * WB); }
       __syncthreads();
     }
   }

@@ -7,8 +7,10 @@
 #define FM_HD __host__ __device__ __forceinline__
 #define FM_D __device__ __forceinline__
 #define FM_HDM __host__ __device__
+#define FM_HDN __host__ __device__ __noinline__     /* big phase bodies called from more than one place: one copy */
 #else
 #define FM_HDM
+#define FM_HDN static
 #define FM_HD static inline
 #define FM_D static inline
 #endif

@@ -96,26 +96,30 @@ struct EnvS {
   int isl_root[NNODE], isl_start[NNODE + 1], need_union;
   unsigned char isl_list[FM_MAXCON], c_node[FM_MAXCON];
   unsigned short queue[FM_QMAX];
-  // ---- per-body scratch of the arm recursions (dead after ph_arm_M) overlaid with the raw contact buffer (written by
-  //      ph_narrow, which the schedule runs after ph_arm_M, and dead after ph_contact_setup)
+  // ---- per-body scratch of the arm recursions, overlaid with the raw contact buffer.  ph_narrow writes the raw contacts while
+  //      ph_arm_M still runs on other warps (fm_derive), so they may only cover what is dead after ph_arm_bwd: the FK scan buffer,
+  //      the per-body inertias / wrenches (d_comp0, d_f0, d_n0) and d_om; d_f, d_n (accumulated wrenches) and d_comp (composite
+  //      inertias) are read by ph_arm_M and lie behind the raw buffer.  The raw buffer is dead after ph_contact_setup.
   union {
     struct {
-      float d_c[NA][FM_NARMBODY][3];
+      float d_unused[NA][FM_NARMBODY][3];
       union {
-        struct { float d_comp0[NA][FM_NARMBODY][10], d_comp[NA][FM_NARMBODY][10]; };   // body phase onwards: own / composite inertia
+        struct { float d_comp0[NA][FM_NARMBODY][10], d_f0[NA][FM_NARMBODY][3], d_n0[NA][FM_NARMBODY][3]; };   // own inertia / wrench (ph_arm_body)
         struct { float d_L[NA][FM_NARMBODY][9], d_p[NA][FM_NARMBODY][3]; };           // FK scan ping-pong buffer (dead after the scan)
       };
       union {
-        struct { float d_om[NA][FM_NARMBODY][3], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3]; };   // until ph_arm_body
-        struct { float d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3]; };                               // accumulated wrench (ph_arm_bwd)
+        struct { float d_om[NA][FM_NARMBODY][3], d_pad0[20], d_al[NA][FM_NARMBODY][3], d_ap[NA][FM_NARMBODY][3]; };   // until ph_arm_body
+        struct { float d_gap[NA][FM_NARMBODY][3], d_pad1[20], d_f[NA][FM_NARMBODY][3], d_n[NA][FM_NARMBODY][3]; };    // accumulated wrench (ph_arm_bwd)
       };
-      float d_f0[NA][FM_NARMBODY][3], d_n0[NA][FM_NARMBODY][3];                                           // own wrench (ph_arm_body)
+      float d_comp[NA][FM_NARMBODY][10];                                               // composite inertia (ph_arm_bwd)
     };
     struct {
       int raw_key[FM_MAXCON], raw_g[FM_MAXCON];
       float raw_d[FM_MAXCON][7];
     };
   };
+  static_assert(sizeof(int) * 2 * FM_MAXCON + sizeof(float) * 7 * FM_MAXCON <= sizeof(float) * (NA * FM_NARMBODY * (3 + 16 + 3) + 20),
+                "the raw contact buffer must end before d_f / d_n / d_comp");
   float force_max;
   // forces of the previous solve, keyed by contact identity (warm start of the dual; persisted in HBM between env steps)
   int prev_n, prev_key[FM_MAXCON];
@@ -300,7 +304,6 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
     Iw[3] = T1[0] * R[3] + T1[1] * R[4] + T1[2] * R[5];
     Iw[4] = T1[0] * R[6] + T1[1] * R[7] + T1[2] * R[8];
     Iw[5] = T1[3] * R[6] + T1[4] * R[7] + T1[5] * R[8];
-    st3(s.d_c[a][b], c);
     float cc = dot3(c, c);
     float* cp = s.d_comp0[a][b];
     cp[0] = ms; cp[1] = ms * c.x; cp[2] = ms * c.y; cp[3] = ms * c.z;
@@ -694,13 +697,19 @@ FM_HD void warm_start_forces(EnvS<NA>& s, int c, int key) {
   for (int r = 0; r < 4; ++r) s.c_f[c][r] = found >= 0 ? s.prev_f[found][r] : 0.f;
 }
 
+#ifndef FM_SETUP_INLINE
+#define FM_SETUP_INLINE FM_HD
+#endif
+// which = 1: contacts without an arm geom (they need nothing of the arm factorisation, so fm_derive runs them beside it),
+// which = 2: contacts of arm geoms (arm-side Jacobians and M^-1 J^T), which = 0: all
 template <int NA, int E>
-FM_HD void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T) {
+FM_SETUP_INLINE void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T, int which) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < FM_MAXCON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ri = w / E;
     int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
     if (ri >= nraw) continue;
+    if (which != 0 && (((s.raw_g[ri] >> 30) & 1) != 0) != (which == 2)) continue;
     int key = s.raw_key[ri];
     // rank = sorted position; arm-side slots are handed out in the same order (deterministic, independent of atomics)
     int rank = 0, slot_base = 0;

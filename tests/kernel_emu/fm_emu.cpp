@@ -23,10 +23,10 @@ struct HostRun {
     else for (int k = 0; k < T; ++k) f((k * 37 + 11) % T);
   }
   // two warp groups that run concurrently on the GPU: here one after the other, in either order (they must be independent)
-  template <int WA, int WB, class PA, class FB> void split(PA progA, FB fB) {
+  template <int WA, int WB, class PA, class PB> void split(PA progA, PB progB) {
     HostRun ra{32 * WA}, rb{32 * (WB ? WB : WA)};
-    if (g_order == 1) { rb([&](int t) { fB(t, rb.T); }); progA(ra, ra.T); }
-    else { progA(ra, ra.T); rb([&](int t) { fB(t, rb.T); }); }
+    if (g_order == 1) { progB(rb, rb.T); progA(ra, ra.T); }
+    else { progA(ra, ra.T); progB(rb, rb.T); }
   }
 };
 
