@@ -74,7 +74,8 @@ FM_HD bool far_sphere_box(f3 sp, float r, f3 bp, const float* bR, f3 hs) {
 
 // box-box: 15-axis separating-axis search, then reference-face clipping (face axes) or closest points of the
 // two edges (edge axes).  Up to 8 contacts.  Same formulation as the oracle, in fp32.
-FM_HD int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 B, RawC* out) {
+// one out-of-line copy: the routine is large, cold for most pairs and called from three places of the narrow phase
+FM_HDN int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 B, RawC* out) {
   f3 pw = p2 - p1;
   f3 pp = rmulT(R1, pw);
   float R[9], Q[9];

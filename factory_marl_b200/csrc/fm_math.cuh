@@ -7,7 +7,7 @@
 #define FM_HD __host__ __device__ __forceinline__
 #define FM_D __device__ __forceinline__
 #define FM_HDM __host__ __device__
-#define FM_HDN __host__ __device__ __noinline__     /* big phase bodies called from more than one place: one copy */
+#define FM_HDN static __host__ __device__ __noinline__     /* big phase bodies called from more than one place: one copy */
 #else
 #define FM_HDM
 #define FM_HDN static

@@ -697,13 +697,10 @@ FM_HD void warm_start_forces(EnvS<NA>& s, int c, int key) {
   for (int r = 0; r < 4; ++r) s.c_f[c][r] = found >= 0 ? s.prev_f[found][r] : 0.f;
 }
 
-#ifndef FM_SETUP_INLINE
-#define FM_SETUP_INLINE FM_HD
-#endif
 // which = 1: contacts without an arm geom (they need nothing of the arm factorisation, so fm_derive runs them beside it),
 // which = 2: contacts of arm geoms (arm-side Jacobians and M^-1 J^T), which = 0: all
 template <int NA, int E>
-FM_SETUP_INLINE void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T, int which) {
+FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T, int which) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < FM_MAXCON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ri = w / E;
