@@ -129,6 +129,8 @@ struct EnvS {
   int pad_[FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 2 (mod 32): the envs of a block start on different (even) shared-memory banks,
                            // and the next item of an odd-stride array falls on the odd ones
 };
+// the envs of a block must start on distinct shared-memory banks: stride = 2 (mod 4) words (checked for both scenes)
+static_assert((sizeof(EnvS<2>) / 4) % 4 == 2 && (sizeof(EnvS<4>) / 4) % 4 == 2, "re-pad EnvS (pad_) after changing its members");
 
 // flags
 #define FM_FLAG_CON_OVERFLOW 1
