@@ -78,13 +78,13 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
         sub([&](int tid) { ph_arm_chol_col<NA, E, 6>(S, tid, TA); });
         sub([&](int tid) { ph_arm_chol_col<NA, E, 7>(S, tid, TA); });
         sub([&](int tid) { ph_arm_chol_col<NA, E, 8>(S, tid, TA); });
-        sub([&](int tid) { ph_arm_minv<NA, E>(S, tid, TA); });
+        sub([&](int tid) { ph_arm_minv<NA, E>(S, tid, TA); ph_arm_rows<NA, E>(S, m, tid, TA); });   // the arm-local rows need no contact
       },
       [&](auto& sub, int TB) {
         sub([&](int tid) { ph_narrow<NA, E>(S, m, cpairs, tid, TB); });
         if (SETUP_IN_B) sub([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, TB, 1); });
       });
-  run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T, SETUP_IN_B ? 2 : 0); ph_arm_rows<NA, E>(S, m, tid, T); });
+  run([&](int tid) { ph_contact_setup<NA, E>(S, m, geom_class, tid, T, SETUP_IN_B ? 2 : 0); });
 }
 
 template <int NA, int E>
