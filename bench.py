@@ -33,9 +33,9 @@ UNIT = "env-steps/s"
 FLOP_PER_ENV_STEP = 2.1e7            # SURVEY.md 8d hand count of the path as MuJoCo runs it (25 solver iterations over ~170 rows)
 FLOP_PER_ENV_STEP_EXECUTED = 4.76e6   # fp32 flop this kernel executes per env-step in the bench workload: ncu fadd + fmul + 2 ffma (profiles/r1m, r1n)
 # dram__bytes_read.sum + dram__bytes_write.sum of fm_step_kernel per env, from the ncu --set full capture
-# profiles/r1n_E14_step_kernel_ncu_raw.csv (8.61 MB read + 0.39 MB written per launch of 2072 envs = one wave of the bench's
+# profiles/r1o_E14_step_kernel_ncu_raw.csv (8.34 MB read + 0.41 MB written per launch of 2072 envs = one wave of the bench's
 # block shape); the 4096-env launch is two such waves
-DRAM_BYTES_PER_ENV_NCU = (8.614e6 + 0.389e6) / 2072   # unchanged in r1o
+DRAM_BYTES_PER_ENV_NCU = (8.341e6 + 0.413e6) / 2072
 
 
 def peaks():
