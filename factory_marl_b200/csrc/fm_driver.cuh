@@ -12,8 +12,8 @@
 
 struct FmDebugDump {   // optional per-launch dump of one env's intermediates after the first derive (tests only)
   int env, ncon, nqueue, flags;
-  int c_g[FM_MAXCON];
-  float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_dist[FM_MAXCON], c_f[FM_MAXCON][4];
+  int c_g[FM_MAXCON_ALL];
+  float c_p[FM_MAXCON_ALL][3], c_n[FM_MAXCON_ALL][3], c_dist[FM_MAXCON_ALL], c_f[FM_MAXCON_ALL][4];
   float body_x[FM_MAX_ARMS][FM_NARMBODY][3], body_R[FM_MAX_ARMS][FM_NARMBODY][9];
   float M[FM_MAX_ARMS][45], bias[FM_MAX_ARMS][9];
   float acc_smooth[61 + 9 * FM_MAX_ARMS], acc[61 + 9 * FM_MAX_ARMS];
@@ -95,7 +95,7 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
   const EnvS<NA>& s = S[e];
   if (stage == 0) {
     d->ncon = s.ncon; d->nqueue = s.nqueue; d->flags = s.flags;
-    for (int c = 0; c < s.ncon && c < FM_MAXCON; ++c) {
+    for (int c = 0; c < s.ncon && c < FmCap<NA>::CON; ++c) {
       d->c_g[c] = ((s.c_key[c] >> 13) << 12) | ((s.c_key[c] >> 4) & 511);
       for (int k = 0; k < 3; ++k) { d->c_p[c][k] = s.c_p[c][k]; d->c_n[c][k] = s.c_n[c][k]; }
     }
@@ -108,7 +108,7 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
     for (int k = 0; k < EnvS<NA>::NV; ++k) d->acc_smooth[k] = s.acc[k];
   } else {
     for (int k = 0; k < EnvS<NA>::NV; ++k) d->acc[k] = s.acc[k];
-    for (int c = 0; c < s.ncon && c < FM_MAXCON; ++c) for (int r = 0; r < 4; ++r) d->c_f[c][r] = s.c_f[c][r];
+    for (int c = 0; c < s.ncon && c < FmCap<NA>::CON; ++c) for (int r = 0; r < 4; ++r) d->c_f[c][r] = s.c_f[c][r];
   }
 }
 

@@ -72,8 +72,9 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     FM_CUDA(cudaMemcpy(h->d_geom_class, h->hm.geom_class.data(), h->hm.geom_class.size() * sizeof(int), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_dump, sizeof(FmDebugDump)));
     const size_t ws_rows = (size_t)cfg->n_envs + 32;   // + padding slots of the last block
-    FM_CUDA(cudaMalloc(&h->d_ws, ws_rows * FM_WS_FLOATS * sizeof(float)));
-    FM_CUDA(cudaMemset(h->d_ws, 0, ws_rows * FM_WS_FLOATS * sizeof(float)));
+    const size_t ws_floats = h->hm.n_arms == 2 ? FmCap<2>::WS : FmCap<4>::WS;
+    FM_CUDA(cudaMalloc(&h->d_ws, ws_rows * ws_floats * sizeof(float)));
+    FM_CUDA(cudaMemset(h->d_ws, 0, ws_rows * ws_floats * sizeof(float)));
     h->st.ws = h->d_ws;
     *out = h;
     return 0;

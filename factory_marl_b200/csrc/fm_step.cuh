@@ -53,8 +53,6 @@ static long long fm_dbg_sat[512] = {0};   // general SAT calls by geom1
 #else
 #define FM_FDIV(a, b) ((a) / (b))
 #endif
-#define FM_WS_FLOATS (FM_MAXARMSIDE * 54 + FM_MAXCON * 4)   // per-env global scratch: as_J, as_B, prev_f
-#define FM_QMAX 96
 #define FM_AROW 10   // equality + up to 9 limit rows per arm
 
 // packed lower-triangular index
@@ -87,15 +85,15 @@ struct EnvS {
   float arow_aref[NA][FM_AROW], arow_R[NA][FM_AROW], arow_f[NA][FM_AROW];
   // ---- contacts
   int ncon, nraw, n_armside, flags, nqueue;
-  int c_side[FM_MAXCON];
-  float c_p[FM_MAXCON][3], c_n[FM_MAXCON][3], c_t1[FM_MAXCON][3], c_mu[FM_MAXCON], c_R[FM_MAXCON], c_W[FM_MAXCON][6];
-  float c_aref[FM_MAXCON][4], c_f[FM_MAXCON][4];
+  int c_side[FmCap<NA>::CON];
+  float c_p[FmCap<NA>::CON][3], c_n[FmCap<NA>::CON][3], c_t1[FmCap<NA>::CON][3], c_mu[FmCap<NA>::CON], c_R[FmCap<NA>::CON], c_W[FmCap<NA>::CON][6];
+  float c_aref[FmCap<NA>::CON][4], c_f[FmCap<NA>::CON][4];
   // rarely / once-per-sub-step touched buffers live in a library-owned global scratch row of this env (L2-resident; see
-  // FM_WS_FLOATS): arm-side Jacobians (3x9) and Minv J^T of contacts that touch an arm, and the previous solve's contact forces
+  // FmCap<NA>::WS): arm-side Jacobians (3x9) and Minv J^T of contacts that touch an arm, and the previous solve's contact forces
   float (*as_J)[27]; float (*as_B)[27]; float (*prev_f)[4];
   int isl_root[NNODE], isl_start[NNODE + 1], need_union;
-  unsigned char isl_list[FM_MAXCON], c_node[FM_MAXCON];
-  unsigned short queue[FM_QMAX];
+  unsigned char isl_list[FmCap<NA>::CON], c_node[FmCap<NA>::CON];
+  unsigned short queue[FmCap<NA>::QUEUE];
   // ---- per-body scratch of the arm recursions, overlaid with the raw contact buffer.  ph_narrow writes the raw contacts while
   //      ph_arm_M still runs on other warps (fm_derive), so they may only cover what is dead after ph_arm_bwd: the FK scan buffer,
   //      the per-body inertias / wrenches (d_comp0, d_f0, d_n0) and d_om; d_f, d_n (accumulated wrenches) and d_comp (composite
@@ -114,18 +112,18 @@ struct EnvS {
       float d_comp[NA][FM_NARMBODY][10];                                               // composite inertia (ph_arm_bwd)
     };
     struct {
-      int raw_key[FM_MAXCON], raw_g[FM_MAXCON];
-      float raw_d[FM_MAXCON][7];
+      int raw_key[FmCap<NA>::CON], raw_g[FmCap<NA>::CON];
+      float raw_d[FmCap<NA>::CON][7];
     };
   };
-  static_assert(sizeof(int) * 2 * FM_MAXCON + sizeof(float) * 7 * FM_MAXCON <= sizeof(float) * (NA * FM_NARMBODY * (3 + 16 + 3) + 20),
+  static_assert(sizeof(int) * 2 * FmCap<NA>::CON + sizeof(float) * 7 * FmCap<NA>::CON <= sizeof(float) * (NA * FM_NARMBODY * (3 + 16 + 3) + 20),
                 "the raw contact buffer must end before d_f / d_n / d_comp");
   float force_max;
   // forces of the previous solve, keyed by contact identity (warm start of the dual; persisted in HBM between env steps)
-  int prev_n, prev_key[FM_MAXCON];
+  int prev_n, prev_key[FmCap<NA>::CON];
   int prev_arow_n[NA], prev_arow_code[NA][FM_AROW];
   float prev_arow_f[NA][FM_AROW];
-  int c_key[FM_MAXCON];
+  int c_key[FmCap<NA>::CON];
   int pad_[FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 2 (mod 32): the envs of a block start on different (even) shared-memory banks,
                            // and the next item of an odd-stride array falls on the odd ones
 };
@@ -489,7 +487,7 @@ FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __rest
       else far = false;
       if (far) continue;
       int slot = FM_ATOMIC_ADD(&s.nqueue, 1);
-      if (slot < FM_QMAX) s.queue[slot] = (unsigned short)(p0 + u * stride); else FM_ATOMIC_OR(&s.flags, FM_FLAG_QUEUE_OVERFLOW);
+      if (slot < FmCap<NA>::QUEUE) s.queue[slot] = (unsigned short)(p0 + u * stride); else FM_ATOMIC_OR(&s.flags, FM_FLAG_QUEUE_OVERFLOW);
     }
   }
 }
@@ -501,7 +499,7 @@ FM_HD void emit(EnvS<NA>& s, int g1, int g2, int side1, int side2, bool armgeom,
   int slot = FM_ATOMIC_ADD(&s.nraw, n);
   for (int k = 0; k < n; ++k) {
     int i = slot + k;
-    if (i >= FM_MAXCON) { FM_ATOMIC_OR(&s.flags, FM_FLAG_CON_OVERFLOW); break; }
+    if (i >= FmCap<NA>::CON) { FM_ATOMIC_OR(&s.flags, FM_FLAG_CON_OVERFLOW); break; }
     s.raw_key[i] = (g1 << 13) | (g2 << 4) | k;
     s.raw_g[i] = side1 | (side2 << FM_SIDE_BITS) | (armgeom ? (1 << 30) : 0);
     s.raw_d[i][0] = rc[k].pos.x; s.raw_d[i][1] = rc[k].pos.y; s.raw_d[i][2] = rc[k].pos.z;
@@ -594,10 +592,10 @@ FM_HD void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __res
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   int mq = 0;
   for (int e = 0; e < E; ++e) mq = S[e].nqueue > mq ? S[e].nqueue : mq;
-  if (mq > FM_QMAX) mq = FM_QMAX;
+  if (mq > FmCap<NA>::QUEUE) mq = FmCap<NA>::QUEUE;
   for (int w = tid; w < mq * FM_NSUB * E; w += T) {
     EnvS<NA>& s = S[w % E]; int rest = w / E; int qi = rest / FM_NSUB, j = rest % FM_NSUB;
-    int nq = s.nqueue < FM_QMAX ? s.nqueue : FM_QMAX;
+    int nq = s.nqueue < FmCap<NA>::QUEUE ? s.nqueue : FmCap<NA>::QUEUE;
     if (qi >= nq) continue;
     unsigned rec = cpairs[s.queue[qi]];
     int c1 = rec & 255, c2 = (rec >> 8) & 255;
@@ -704,9 +702,9 @@ FM_HD void warm_start_forces(EnvS<NA>& s, int c, int key) {
 template <int NA, int E>
 FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __restrict__ geom_class, int tid, int T, int which) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-  for (int w = tid; w < FM_MAXCON * E; w += T) {
+  for (int w = tid; w < FmCap<NA>::CON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ri = w / E;
-    int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
+    int nraw = s.nraw < FmCap<NA>::CON ? s.nraw : FmCap<NA>::CON;
     if (ri >= nraw) continue;
     if (which != 0 && (((s.raw_g[ri] >> 30) & 1) != 0) != (which == 2)) continue;
     int key = s.raw_key[ri];
@@ -740,7 +738,7 @@ FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __rest
         int a = ix >> 4, b = ix & 15;
         invw += m.ab_invw[b];
         int sl = slot_base++;
-        if (sl >= FM_MAXARMSIDE) { FM_ATOMIC_OR(&s.flags, FM_FLAG_ARMSIDE_OVERFLOW); sds[sdi] = pack_side(FM_SIDE_STATIC, 0, 0); continue; }
+        if (sl >= FmCap<NA>::ARMSIDE) { FM_ATOMIC_OR(&s.flags, FM_FLAG_ARMSIDE_OVERFLOW); sds[sdi] = pack_side(FM_SIDE_STATIC, 0, 0); continue; }
         sds[sdi] = pack_side(ty, ix, sl);
         float* J = s.as_J[sl]; float* Bv = s.as_B[sl];
         f3 dirs[3] = {n, t1, t2};
@@ -863,7 +861,7 @@ FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
-    int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
+    int nraw = s.nraw < FmCap<NA>::CON ? s.nraw : FmCap<NA>::CON;
     s.ncon = nraw;
     FM_DBG(fm_dbg_cnt[0]++; fm_dbg_cnt[1] += nraw; fm_dbg_cnt[2] += s.nqueue; fm_dbg_cnt[3] += s.need_union; for (int k = 0; k < FM_NCUBE; ++k) fm_dbg_cnt[26] += !s.cube_sleep[k];)
     if (!s.need_union) continue;
@@ -884,10 +882,10 @@ template <int NA, int E>
 FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   const int NN = EnvS<NA>::NNODE;
-  for (int w = tid; w < (FM_MAXCON + NN + 1) * E; w += T) {
+  for (int w = tid; w < (FmCap<NA>::CON + NN + 1) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
-    int nraw = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
-    if (i < FM_MAXCON) {
+    int nraw = s.nraw < FmCap<NA>::CON ? s.nraw : FmCap<NA>::CON;
+    if (i < FmCap<NA>::CON) {
       if (i >= nraw) continue;
       int nd = s.c_node[i];
       if (nd == 255) continue;
@@ -896,7 +894,7 @@ FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
       for (int c = 0; c < nraw; ++c) { int n2 = s.c_node[c]; if (n2 == 255) continue; int r2 = s.isl_root[n2]; pos += (r2 < r || (r2 == r && c < i)) ? 1 : 0; }
       s.isl_list[pos] = (unsigned char)i;
     } else {
-      int node = i - FM_MAXCON;      // 0..NN: start offset of island `node` (NN = end sentinel)
+      int node = i - FmCap<NA>::CON;      // 0..NN: start offset of island `node` (NN = end sentinel)
       int cnt = 0;
       for (int c = 0; c < nraw; ++c) { int n2 = s.c_node[c]; if (n2 == 255) continue; cnt += (s.isl_root[n2] < node) ? 1 : 0; }
       s.isl_start[node] = cnt;
@@ -913,7 +911,7 @@ FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   const int per = 1 + FM_NCUBE + 9 * NA;
   for (int w = tid; w < per * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
-    const int ncon = s.nraw < FM_MAXCON ? s.nraw : FM_MAXCON;
+    const int ncon = s.nraw < FmCap<NA>::CON ? s.nraw : FmCap<NA>::CON;
     if (i == 0) {
       float c = clampf(s.ctrl_target[0], m.ctrl_lo[0], m.ctrl_hi[0]);
       float f = m.belt_kv * (c - s.belt_v) - m.belt_damp * s.belt_v;
@@ -1059,7 +1057,7 @@ FM_HD float arm_rows_visit(EnvS<NA>& s, int a, int mode) {
 template <int NA, int E>
 FM_HD void ph_check(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-  for (int w = tid; w < FM_MAXCON * E; w += T) {
+  for (int w = tid; w < FmCap<NA>::CON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
     if (c >= s.ncon) continue;
     c_res(s, c) = contact_visit(s, m, c, false);
@@ -1255,7 +1253,7 @@ FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 template <int NA, int E>
 FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
-  for (int w = tid; w < FM_MAXCON * E; w += T) {
+  for (int w = tid; w < FmCap<NA>::CON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
     if (c >= s.ncon || !((s.c_side[c] >> 30) & 1)) continue;
     const float* f = s.c_f[c]; float mu = s.c_mu[c];
@@ -1313,13 +1311,13 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 template <int NA, int E>
 FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
-  for (int w = tid; w < (FM_MAXCON + NA) * E; w += T) {
+  for (int w = tid; w < (FmCap<NA>::CON + NA) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
-    if (c < FM_MAXCON) {
+    if (c < FmCap<NA>::CON) {
       if (c == 0) s.prev_n = s.ncon;
       if (c < s.ncon) { s.prev_key[c] = s.c_key[c]; for (int r = 0; r < 4; ++r) s.prev_f[c][r] = s.c_f[c][r]; }
     } else {
-      int a = c - FM_MAXCON;
+      int a = c - FmCap<NA>::CON;
       s.prev_arow_n[a] = s.arow_n[a];
       for (int r = 0; r < s.arow_n[a]; ++r) { s.prev_arow_code[a][r] = s.arow_code[a][r]; s.prev_arow_f[a][r] = s.arow_f[a][r]; }
     }

@@ -24,12 +24,12 @@ struct Lay {
   static const int I_IN = 0, I_OUT = 10, I_NIN = 20, I_NOUT = 21, I_STEP = 22, I_SINCE = 23, I_FAIL = 24, I_OUTCNT = 25,
                    I_SCORE = 26, I_LAST_SCORE = 28, I_EP_LEN = 30, I_FSM_STATE = 31, I_FSM_CNT = I_FSM_STATE + NA,
                    I_FSM_TGT = I_FSM_CNT + NA, I_IGNORE = I_FSM_TGT + NA, I_FLAGS = I_IGNORE + NA * NA, I_EPISODES = I_FLAGS + 1,
-                   I_MAXCON = I_EPISODES + 1, I_PREV_N = I_MAXCON + 1, I_PREV_KEY = I_PREV_N + 1, I_PREV_AN = I_PREV_KEY + FM_MAXCON,
+                   I_MAXCON = I_EPISODES + 1, I_PREV_N = I_MAXCON + 1, I_PREV_KEY = I_PREV_N + 1, I_PREV_AN = I_PREV_KEY + FmCap<NA>::CON,
                    I_PREV_ACODE = I_PREV_AN + NA, NI = I_PREV_ACODE + FM_AROW * NA;
   FM_HDM static int obs_dim(int env_class) { return NA * 24 + 130 + ((env_class == FM_ENV_PAUSE_TOGGLE || env_class == FM_ENV_BACKUP_TOGGLE) ? 8 * NA : 0); }
 };
 
-struct FmStatePtrs { float* f; double* d; int* i; unsigned long long* rng; int n; float* ws; /* library-owned scratch [n][FM_WS_FLOATS] */ };
+struct FmStatePtrs { float* f; double* d; int* i; unsigned long long* rng; int n; float* ws; /* library-owned scratch [n][FmCap<NA>::WS] */ };
 
 // per-env task scratch kept in shared memory next to EnvS
 struct TaskS {
@@ -112,7 +112,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
   }
   for (int w = tid; w < E; w += T) {
     int env = env0 + w;
-    float* ws = st.ws + (size_t)env * FM_WS_FLOATS;    // the scratch has rows for the padding slots too
+    float* ws = st.ws + (size_t)env * FmCap<NA>::WS;    // the scratch has rows for the padding slots too
     if (env >= N) env = N - 1;
     TS[w].conveyor_speed = st.d[(size_t)L::D_CONV * N + env];
     TS[w].spawn_freq = st.d[(size_t)L::D_SPAWN_FREQ * N + env];
@@ -120,8 +120,8 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     S[w].conveyor_speed = (float)TS[w].conveyor_speed;
     S[w].flags = 0; S[w].force_max = 0.f;
     S[w].as_J = reinterpret_cast<float (*)[27]>(ws);
-    S[w].as_B = reinterpret_cast<float (*)[27]>(ws + FM_MAXARMSIDE * 27);
-    S[w].prev_f = reinterpret_cast<float (*)[4]>(ws + FM_MAXARMSIDE * 54);
+    S[w].as_B = reinterpret_cast<float (*)[27]>(ws + FmCap<NA>::ARMSIDE * 27);
+    S[w].prev_f = reinterpret_cast<float (*)[4]>(ws + FmCap<NA>::ARMSIDE * 54);
   }
 }
 

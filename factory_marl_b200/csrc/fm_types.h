@@ -12,6 +12,15 @@
 #define FM_MAXCON 56        // contacts per env
 #define FM_MAXARMSIDE 40    // contact sides that touch an arm (a grasped cube alone makes 16+); stored in global scratch (each stores 3x9 Jacobian + 3x9 Minv J^T)
 #define FM_MAX_ARMS 4
+#define FM_MAXCON_ALL 96   // largest per-scene contact capacity (debug dump arrays)
+// per-scene capacities: FM_MAXCON / FM_MAXARMSIDE are the two-arm values; four arms crash into each other and the table far more
+// often (and have the shared memory to spare: one block of 7 envs per SM)
+template <int NA> struct FmCap {
+  static constexpr int CON = NA <= 2 ? FM_MAXCON : FM_MAXCON_ALL;         // contacts per env
+  static constexpr int ARMSIDE = NA <= 2 ? FM_MAXARMSIDE : 64;            // contact sides on an arm (6-bit slot)
+  static constexpr int QUEUE = NA <= 2 ? 96 : 160;                        // cluster pairs queued for the narrow phase
+  static constexpr int WS = ARMSIDE * 54 + CON * 4;                       // floats of the env's global scratch row: as_J, as_B, prev_f
+};
 #define FM_NCLASS 4
 
 enum { FM_CL_PLANE = 0, FM_CL_SBOX = 1, FM_CL_BELT = 2, FM_CL_CUBE = 3, FM_CL_ARM = 4 };

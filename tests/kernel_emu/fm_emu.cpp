@@ -97,7 +97,7 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
     { int e = cfg->envs_per_block; h->E = (e == 1 || e == 7 || (cfg->n_arms == 2 && (e == 2 || e == 14))) ? e : 4; }   // same shapes as the library (+ E = 2)
-    h->ws.assign(((size_t)cfg->n_envs + 32) * FM_WS_FLOATS, 0.f);
+    h->ws.assign(((size_t)cfg->n_envs + 32) * (cfg->n_arms == 2 ? FmCap<2>::WS : FmCap<4>::WS), 0.f);
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, h->ws.data()};
     *out = h; return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
