@@ -179,3 +179,18 @@ def test_mean_collected_objects_within_oracle_ci():
           (mean_total, st["mean_total"], lo, hi, mean_len, st["mean_length"], st["ci95_length"]))
     assert lo <= mean_total <= hi, (mean_total, lo, hi)
     assert st["ci95_length"][0] <= mean_len <= st["ci95_length"][1], (mean_len, st["ci95_length"])
+
+
+def test_four_arm_capacities_hold_under_ik_toggling():
+    """four arms crash into the table and into each other far more often than two: with the four-arm capacities (FmCap<4>: 96
+    contacts, 64 arm-side Jacobians, 160 queued pairs) no capacity flag may come up in 50 steps of random IK toggling"""
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    n = 512
+    env = FactoryVecEnv("PauseIKToggleEnv", num_envs=n, num_arms=4, seeds=list(range(42, 42 + n)))
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(50):
+        obs, rew, term, _ = env.step(torch.randint(0, 2, (n, 4), device="cuda", generator=gen, dtype=torch.int32))
+    assert int(env.core.i[env.core.off("I_FLAGS")].max()) == 0
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert int(env.core.i[env.core.off("I_MAXCON")].max()) > 0
