@@ -143,11 +143,10 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
   fm_derive<NA, E, TW>(run, S, m, cpairs, geom_class, cfg.sleep_hidden);
   run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
   const double hd = cfg.dt / cfg.frame_skip;
-  const float alpha = (float)(hd / (hd + cfg.pt_time));   // base_env.py:209-211
   const int nsub = ar.mode == 0 ? cfg.frame_skip : ar.n_substeps;
   for (int t = 0; t < nsub; ++t) {
     if (t > 0) fm_derive<NA, E, TW>(run, S, m, cpairs, geom_class, cfg.sleep_hidden);
-    run([&](int tid) { ph_island_union<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, alpha); });
+    run([&](int tid) { ph_island_union<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, t < FM_MAX_FRAME_SKIP ? cfg.pt1_pow[t] : (float)pow(1.0 - hd / (hd + cfg.pt_time), t + 1.0)); });
     run([&](int tid) { ph_island_lists<NA, E>(S, tid, T); ph_smooth<NA, E>(S, m, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 1); });

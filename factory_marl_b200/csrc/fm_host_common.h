@@ -24,6 +24,7 @@ inline FmEnvCfg fm_make_cfg(const fm_config& c, double h) {
   e.spawn_freq_increase = c.spawn_freq_increase;
   e.w_gripper_cube = c.gripper_to_closest_cube_reward_factor; e.w_cube_bucket = c.closest_cube_to_bucket_reward_factor;
   e.w_action_norm = c.small_action_norm_reward_factor; e.base_reward = c.base_reward;
+  { const double hd = e.dt / e.frame_skip, alpha = hd / (hd + c.pt_time); for (int k = 0; k < FM_MAX_FRAME_SKIP; ++k) e.pt1_pow[k] = (float)std::pow(1.0 - alpha, k + 1.0); }
   return e;
 }
 
@@ -45,7 +46,7 @@ inline int fm_field_offset_t(const char* name) {
 #define FM_OFF(x) if (s == #x) return L::x;
   FM_OFF(F_BELT_Q) FM_OFF(F_BELT_V) FM_OFF(F_CUBE_Q) FM_OFF(F_CUBE_V) FM_OFF(F_ARM_Q) FM_OFF(F_ARM_V) FM_OFF(F_CTRL_T)
   FM_OFF(F_ACC_WS) FM_OFF(F_PRE_Q) FM_OFF(F_PRE_V) FM_OFF(F_LAST_GD) FM_OFF(F_LAST_BD) FM_OFF(F_IK_ACT) FM_OFF(F_LAST_ARM_ACT)
-  FM_OFF(F_IK_LAST_CTRL) FM_OFF(F_IK_MOVE_START) FM_OFF(F_SITE) FM_OFF(F_EP_RET) FM_OFF(F_PREV_F) FM_OFF(F_PREV_AF) FM_OFF(NF)
+  FM_OFF(F_IK_LAST_CTRL) FM_OFF(F_IK_MOVE_START) FM_OFF(F_SITE) FM_OFF(F_EP_RET) FM_OFF(F_PREV_F) FM_OFF(F_PREV_AF) FM_OFF(F_CUBE_QLO) FM_OFF(F_ARM_QLO) FM_OFF(NF)
   FM_OFF(D_CONV) FM_OFF(D_SPAWN_FREQ) FM_OFF(D_PLAY_TIME) FM_OFF(ND)
   FM_OFF(I_IN) FM_OFF(I_OUT) FM_OFF(I_NIN) FM_OFF(I_NOUT) FM_OFF(I_STEP) FM_OFF(I_SINCE) FM_OFF(I_FAIL) FM_OFF(I_OUTCNT)
   FM_OFF(I_SCORE) FM_OFF(I_LAST_SCORE) FM_OFF(I_EP_LEN) FM_OFF(I_FSM_STATE) FM_OFF(I_FSM_CNT) FM_OFF(I_FSM_TGT) FM_OFF(I_IGNORE)
@@ -63,7 +64,8 @@ inline void fm_view_get(const float* f, int N, const fm_state_view* v) {
   if (v->qpos) {
     v->qpos[0] = F(L::F_BELT_Q);
     for (int k = 0; k < 70; ++k) v->qpos[1 + k] = F(L::F_CUBE_Q + k);
-    for (int k = 0; k < 9 * NA; ++k) v->qpos[71 + k] = F(L::F_ARM_Q + k);
+    for (int k = 0; k < 30; ++k) v->qpos[1 + 7 * (k / 3) + k % 3] += F(L::F_CUBE_QLO + k);   // compensated low-order part
+    for (int k = 0; k < 9 * NA; ++k) v->qpos[71 + k] = F(L::F_ARM_Q + k) + F(L::F_ARM_QLO + k);
   }
   if (v->qvel) {
     v->qvel[0] = F(L::F_BELT_V);
@@ -80,7 +82,8 @@ inline void fm_view_set(float* f, int N, const fm_state_view* v) {
   if (v->qpos) {
     W(L::F_BELT_Q, v->qpos[0]);
     for (int k = 0; k < 70; ++k) { W(L::F_CUBE_Q + k, v->qpos[1 + k]); W(L::F_PRE_Q + k, v->qpos[1 + k]); }
-    for (int k = 0; k < 9 * NA; ++k) W(L::F_ARM_Q + k, v->qpos[71 + k]);
+    for (int k = 0; k < 30; ++k) W(L::F_CUBE_QLO + k, (v->qpos[1 + 7 * (k / 3) + k % 3] - (double)(float)v->qpos[1 + 7 * (k / 3) + k % 3]));   // what float drops of the fp64 position
+    for (int k = 0; k < 9 * NA; ++k) { W(L::F_ARM_Q + k, v->qpos[71 + k]); W(L::F_ARM_QLO + k, v->qpos[71 + k] - (double)(float)v->qpos[71 + k]); }
   }
   if (v->qvel) {
     W(L::F_BELT_V, v->qvel[0]);

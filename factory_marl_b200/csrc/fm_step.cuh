@@ -54,12 +54,18 @@ static long long fm_dbg_sat[512] = {0};   // general SAT calls by geom1
 #define FM_FDIV(a, b) ((a) / (b))
 #endif
 #define FM_AROW 10   // equality + up to 9 limit rows per arm
+// Box-box contacts are twice as soft in the reference as MuJoCo's documented regulariser (R = 2 mu^2 (1-d)/d diagApprox, four
+// pyramid rows on each of the four face-clipping points) predicts: every resting cube in runs/*.zip:_last_obs (90 samples, belt
+// and table) sits 2.28e-6 m (belt) / 4.2e-7 m (table) deep, exactly 2x the documented 1.14e-6 / 2.04e-7, independent of mass.
+// Which mjc_BoxBox / mj_makeImpedance detail causes it cannot be read here (MuJoCo is absent), so the factor is CALIBRATED to
+// that reference-held data (tests/test_ref_fixtures.py) and applied to box-box pairs only, in the oracle and here alike.
+#define FM_BOXBOX_RSCALE 2.0f
 
 // packed lower-triangular index
 FM_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 #ifndef FM_ENVS_PAD
-#define FM_ENVS_PAD 5
+#define FM_ENVS_PAD 1
 #endif
 template <int NA>
 struct EnvS {
@@ -67,6 +73,7 @@ struct EnvS {
   // ---- state (persisted in HBM between env steps)
   float belt_q, belt_v;
   float cube_q[FM_NCUBE][7], cube_v[FM_NCUBE][6];
+  float cube_qlo[FM_NCUBE][3];   // low-order part of the cube positions (compensated integration, see ph_integrate)
   float arm_q[NA][9], arm_v[NA][9];
   float ctrl_target[NU], ctrl[NU];
   float conveyor_speed;
@@ -91,6 +98,9 @@ struct EnvS {
   // rarely / once-per-sub-step touched buffers live in a library-owned global scratch row of this env (L2-resident; see
   // FmCap<NA>::WS): arm-side Jacobians (3x9) and Minv J^T of contacts that touch an arm, and the previous solve's contact forces
   float (*as_J)[27]; float (*as_B)[27]; float (*prev_f)[4];
+  float* ct_d0;   // ctrl_target - ctrl at the start of the control step (closed-form PT1 filter, ph_ctrl); followed by arm_qlo
+  // low-order part of the arm joint positions (compensated integration like cube_qlo; lives in the global scratch row)
+  FM_HDM float* arm_qlo(int a) const { return ct_d0 + (1 + 8 * FM_MAX_ARMS) + 9 * a; }
   int isl_root[NNODE], isl_start[NNODE + 1], need_union;
   unsigned char isl_list[FmCap<NA>::CON], c_node[FmCap<NA>::CON];
   unsigned short queue[FmCap<NA>::QUEUE];
@@ -724,7 +734,8 @@ FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __rest
     f3 p = mk3(s.raw_d[ri][0], s.raw_d[ri][1], s.raw_d[ri][2]), n = mk3(s.raw_d[ri][3], s.raw_d[ri][4], s.raw_d[ri][5]);
     float dist = s.raw_d[ri][6];
     f3 t1, t2; make_frame3(n, t1, t2);
-    const float* pp = m.pair_param[geom_class[g1]][geom_class[g2]];
+    const int gc1 = geom_class[g1], gc2 = geom_class[g2];
+    const float* pp = m.pair_param[gc1 & 15][gc2 & 15];
     float mu = pp[0];
     // arm sides: Jacobian rows and Minv J^T
     int sds[2] = {sd1, sd2};
@@ -765,6 +776,7 @@ FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __rest
     float dA = invw * (1.f + mu * mu);
     float R0 = fmaxf(1e-15f, (1.f - imp) * dA / imp);
     float Rpy = 2.f * mu * mu * R0;           // [3P] pyramidal regulariser
+    if (gc1 & gc2 & 16) Rpy *= FM_BOXBOX_RSCALE;   // box-box pairs: calibrated to the reference's rest depth (see the define)
     s.c_R[c] = Rpy;
     SideW A, Bs;
     side_prepare(s, m, sds[0], -1.f, p, n, t1, t2, A);
@@ -1282,7 +1294,18 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       float* a = &s.acc[1 + 6 * k]; float* v = s.cube_v[k]; float* q = s.cube_q[k];
       f3 al = rmulT(s.cube_R[k], mk3(a[3], a[4], a[5]));      // world-frame angular acceleration -> body frame (free-joint qvel convention)
       v[0] += h * a[0]; v[1] += h * a[1]; v[2] += h * a[2]; v[3] += h * al.x; v[4] += h * al.y; v[5] += h * al.z;
-      q[0] += h * v[0]; q[1] += h * v[1]; q[2] += h * v[2];
+      // Compensated position update (Fast2Sum): a float near 1.13 m resolves 1.2e-7 m, but a resting cube's penetration is
+      // 2.3e-6 m and its per-sub-step travel h*v far below one ulp, so a plain `q += h v` freezes z up to 5e-7 m away from the
+      // equilibrium with a residual velocity of 4e-5 m/s.  The increments that do not fit are carried in cube_qlo (part of the
+      // persisted state; zeroed whenever the task manager or fm_set_state writes the pose).
+      float* ql = s.cube_qlo[k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float inc = h * v[c] + ql[c];
+        float nq = q[c] + inc;
+        ql[c] = inc - (nq - q[c]);
+        q[c] = nq;
+      }
       f3 wv = mk3(v[3], v[4], v[5]);
       float wn = norm3(wv);
       q4 qq = qnormf(mkq(q[3], q[4], q[5], q[6]));
@@ -1302,7 +1325,15 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
         y[r] = sum;
       }
       chol9_solve(s.Li[a], s.chol_d[a][1], y);
-      for (int r = 0; r < 9; ++r) { s.arm_v[a][r] += h * y[r]; s.arm_q[a][r] += h * s.arm_v[a][r]; }
+      float* ql = s.arm_qlo(a);
+      for (int r = 0; r < 9; ++r) {
+        s.arm_v[a][r] += h * y[r];
+        // compensated like the cube positions: a joint creeping to its target at < 6e-5 rad/s would otherwise stall 1e-5 rad short
+        float q0 = s.arm_q[a][r], inc = h * s.arm_v[a][r] + ql[r];
+        float nq = q0 + inc;
+        ql[r] = inc - (nq - q0);
+        s.arm_q[a][r] = nq;
+      }
     }
   }
 }
@@ -1324,15 +1355,18 @@ FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
   }
 }
 
-// phase: PT1 control filter (base_env.py:209-215) and per-substep counters reset
+// phase: PT1 control filter (base_env.py:209-215).  The command is constant over the control step, so the recursion
+// ctrl_target += (ctrl - ctrl_target) * alpha has the closed form ctrl + d0 (1 - alpha)^(k+1) with d0 = ctrl_target - ctrl at the
+// start of the step.  Evaluated that way because the recursion stalls in fp32 once its increment falls below half an ulp
+// (1.2e-5 short of a target of 1.0: an idle arm then hangs 1e-5 rad off the reference's pose, tests/ref_cases.py).
 template <int NA, int E>
-FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float alpha) {
+FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float pk) {
   FM_ASSUME_SHARED(S);
   const int NU = EnvS<NA>::NU;
   for (int w = tid; w < NU * E; w += T) {
     EnvS<NA>& s = S[w % E]; int u = w / E;
     if (u == 0) { s.ctrl_target[0] = -s.conveyor_speed; }
-    else s.ctrl_target[u] += (s.ctrl[u] - s.ctrl_target[u]) * alpha;
+    else s.ctrl_target[u] = s.ctrl[u] + s.ct_d0[u] * pk;
   }
 }
 template <int NA, int E>

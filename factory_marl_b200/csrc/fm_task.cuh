@@ -17,7 +17,7 @@ struct Lay {
                    F_PRE_Q = F_ACC_WS + 1, F_PRE_V = F_PRE_Q + 70, F_LAST_GD = F_PRE_V + 60, F_LAST_BD = F_LAST_GD + NA,
                    F_IK_ACT = F_LAST_BD + NA, F_LAST_ARM_ACT = F_IK_ACT + 8 * NA, F_IK_LAST_CTRL = F_LAST_ARM_ACT + 8 * NA,
                    F_IK_MOVE_START = F_IK_LAST_CTRL + 8 * NA, F_SITE = F_IK_MOVE_START + 3 * NA, F_EP_RET = F_SITE + 3 * NA,
-                   F_PREV_F = F_EP_RET + 1, F_PREV_AF = F_PREV_F, NF = F_PREV_AF + FM_AROW * NA;
+                   F_PREV_F = F_EP_RET + 1, F_PREV_AF = F_PREV_F, F_CUBE_QLO = F_PREV_AF + FM_AROW * NA, F_ARM_QLO = F_CUBE_QLO + 30, NF = F_ARM_QLO + 9 * NA;
   // double fields
   static const int D_CONV = 0, D_SPAWN_FREQ = 1, D_PLAY_TIME = 2, ND = 3;
   // int fields
@@ -37,6 +37,7 @@ struct TaskS {
   double conveyor_speed, spawn_freq, play_time;
   float reward, ep_ret;
   int terminated, out_of_reach, force_term, done_prev;
+  int stale, index_err;   // see ph_task: dm_control dirty flag at the end of the task step; flagged IndexError case of task_utils.py:110
   int order[FM_NCUBE];
   float last_gd[FM_MAX_ARMS], last_bd[FM_MAX_ARMS];
   float site[FM_MAX_ARMS][3];
@@ -90,6 +91,8 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     else if (fidx < L::F_IK_ACT) TS[e].last_bd[fidx - L::F_LAST_BD] = v;
     else if (fidx == L::F_EP_RET) TS[e].ep_ret = v;
     else if (fidx >= L::F_PREV_F && fidx < L::F_PREV_AF) { }   // contact forces persist in the library scratch (st.ws)
+    else if (fidx >= L::F_ARM_QLO) { }   // into the global scratch row below
+    else if (fidx >= L::F_CUBE_QLO) (&s.cube_qlo[0][0])[fidx - L::F_CUBE_QLO] = v;
     else if (fidx >= L::F_PREV_AF) (&s.prev_arow_f[0][0])[fidx - L::F_PREV_AF] = v;
   }
   for (int w = tid; w < L::NI * E; w += T) {
@@ -122,6 +125,8 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     S[w].as_J = reinterpret_cast<float (*)[27]>(ws);
     S[w].as_B = reinterpret_cast<float (*)[27]>(ws + FmCap<NA>::ARMSIDE * 27);
     S[w].prev_f = reinterpret_cast<float (*)[4]>(ws + FmCap<NA>::ARMSIDE * 54);
+    S[w].ct_d0 = ws + FmCap<NA>::ARMSIDE * 54 + FmCap<NA>::CON * 4;
+    for (int k = 0; k < 9 * NA; ++k) S[w].arm_qlo(0)[k] = st.f[(size_t)(L::F_ARM_QLO + k) * N + env];
   }
 }
 
@@ -176,6 +181,7 @@ FM_HD void ph_action(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg
       v = act_i[(size_t)env * NA + a] == 1 ? ikv : dp[k];
     }
     s.ctrl[u] = clampf(v, lo, hi);
+    s.ct_d0[u] = s.ctrl_target[u] - s.ctrl[u];     // same lane reads it back in ph_ctrl
   }
   // action-norm term of the progress reward (environments.py:371-373)
   for (int w = tid; w < E; w += T) {
@@ -209,6 +215,7 @@ FM_HD void task_hide(EnvS<NA>& s, TaskS& t, int k) {
   float* q = s.cube_q[k]; float* v = s.cube_v[k];
   q[0] = 5.0f; q[1] = (float)(t.out_counter * 0.2); q[2] = 1.0f; q[3] = 1.f; q[4] = 0.f; q[5] = 0.f; q[6] = 0.f;
   for (int i = 0; i < 6; ++i) v[i] = 0.f;
+  for (int i = 0; i < 3; ++i) s.cube_qlo[k][i] = 0.f;
   t.out_counter++;
 }
 template <int NA>
@@ -217,11 +224,12 @@ FM_HD void task_remove_in(TaskS& t, int idx) { for (int i = idx; i + 1 < t.n_in;
 template <int NA>
 FM_HD void task_reset_state(EnvS<NA>& s, TaskS& t, const FmEnvCfg& cfg) {
   s.belt_q = 0.f; s.belt_v = 0.f;
-  for (int a = 0; a < NA; ++a) for (int d = 0; d < 9; ++d) { s.arm_q[a][d] = 0.f; s.arm_v[a][d] = 0.f; }
+  for (int a = 0; a < NA; ++a) for (int d = 0; d < 9; ++d) { s.arm_q[a][d] = 0.f; s.arm_v[a][d] = 0.f; s.arm_qlo(a)[d] = 0.f; }
   for (int k = 0; k < FM_NCUBE; ++k) {
     float* q = s.cube_q[k]; float* v = s.cube_v[k];
     q[0] = 4.0f; q[1] = (float)(0.0 + k * 0.2); q[2] = 1.0f; q[3] = 1.f; q[4] = 0.f; q[5] = 0.f; q[6] = 0.f;
     for (int i = 0; i < 6; ++i) v[i] = 0.f;
+    for (int i = 0; i < 3; ++i) s.cube_qlo[k][i] = 0.f;
     t.out_scene[k] = k;
   }
   t.n_out = FM_NCUBE; t.n_in = 0;
@@ -246,6 +254,8 @@ FM_HD void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& 
     EnvS<NA>& s = S[w]; TaskS& t = TS[w];
     // TaskManager.step (task_utils.py:135-144)
     int spawn_steps = (int)(1.0 / (0.1 * t.spawn_freq));
+    bool dirty = false;
+    t.index_err = 0;
     if (t.step_counter == 0 || t.since_spawn >= spawn_steps) {
       if (t.n_out > 0) {
         int k = t.out_scene[0];
@@ -255,25 +265,39 @@ FM_HD void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& 
         for (int i = 0; i < 4; ++i) r4[i] = st.rng[(size_t)i * N + env];
         float* q = s.cube_q[k];
         q[0] = 0.f; q[1] = 1.f; q[2] = 2.f;
+        for (int i = 0; i < 3; ++i) s.cube_qlo[k][i] = 0.f;
         for (int i = 0; i < 4; ++i) q[3 + i] = (float)pcg64_uniform(r4);
         for (int i = 0; i < 2; ++i) st.rng[(size_t)i * N + env] = r4[i];
         t.in_scene[t.n_in++] = k;
+        dirty = true;
       }
       t.since_spawn = 0;
     }
-    // _check_states (task_utils.py:79-113)
+    // _check_states (task_utils.py:79-113).  `dirty` follows dm_control's mjcf.Physics: every write through a binding (spawn,
+    // hide) marks the physics dirty, and reading a derived quantity through a binding — `physics.bind(bucket).xpos` at
+    // task_utils.py:101 and environments.py:363 — runs mj_forward first [3P].  If the flag survives the task step, the next
+    // physics.step() starts from contacts / Jacobians of the pre-edit pose (stale); otherwise from the edited one.
     for (int idx = t.n_in - 1; idx >= 0; --idx) {
       const float* q = s.cube_q[t.in_scene[idx]];
       bool out = fabs((double)q[0]) > 1.2 || (double)q[1] < -1.5 || (double)q[2] < 0.9;
-      if (out) { int k = t.in_scene[idx]; task_remove_in<NA>(t, idx); task_hide(s, t, k); t.fail++; }
+      if (out) { int k = t.in_scene[idx]; task_remove_in<NA>(t, idx); task_hide(s, t, k); t.fail++; dirty = true; }
     }
-    for (int b = 0; b < 2; ++b) {
-      double bx = m.bucket_pos[b][0], by = m.bucket_pos[b][1], bz = m.bucket_pos[b][2];
-      double sx = m.bucket_size[b][0], sy = m.bucket_size[b][1], sz = m.bucket_size[b][2];
-      for (int idx = t.n_in - 1; idx >= 0; --idx) {
-        const float* q = s.cube_q[t.in_scene[idx]];
-        bool in_x = fabs((double)q[0] - bx) <= 0.6 * sx, in_y = fabs((double)q[1] - by) <= 0.6 * sy, in_z = (double)q[2] - bz - sz / 2 <= 0.07;
-        if (in_x && in_y && in_z) { int k = t.in_scene[idx]; task_remove_in<NA>(t, idx); task_hide(s, t, k); t.score[b]++; }
+    if (t.n_in > 0) {
+      // ONE position snapshot for both buckets (task_utils.py:97); bucket 1's hit indices are applied to the list as bucket 0's
+      // removals left it — the reference's index mismatch, reproduced (an index past the end raises IndexError there: flagged)
+      float snap[FM_NCUBE][3]; const int nsnap = t.n_in;
+      for (int i = 0; i < nsnap; ++i) for (int c = 0; c < 3; ++c) snap[i][c] = s.cube_q[t.in_scene[i]][c];
+      for (int b = 0; b < 2; ++b) {
+        dirty = false;                                      // physics.bind(b).xpos
+        double bx = m.bucket_pos[b][0], by = m.bucket_pos[b][1], bz = m.bucket_pos[b][2];
+        double sx = m.bucket_size[b][0], sy = m.bucket_size[b][1], sz = m.bucket_size[b][2];
+        for (int idx = nsnap - 1; idx >= 0; --idx) {
+          const float* q = snap[idx];
+          bool in_x = fabs((double)q[0] - bx) <= 0.6 * sx, in_y = fabs((double)q[1] - by) <= 0.6 * sy, in_z = (double)q[2] - bz - sz / 2 <= 0.07;
+          if (!(in_x && in_y && in_z)) continue;
+          if (idx >= t.n_in) { t.index_err = 1; continue; }
+          int k = t.in_scene[idx]; task_remove_in<NA>(t, idx); task_hide(s, t, k); t.score[b]++; dirty = true;
+        }
       }
     }
     t.step_counter++; t.since_spawn++;
@@ -288,6 +312,7 @@ FM_HD void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& 
     float score_reward = (float)((t.score[0] + t.score[1]) - (t.last_score[0] + t.last_score[1]));
     float reward = score_reward;
     bool progress = cfg.env_class >= FM_ENV_SINGLE_FULL && cfg.env_class <= FM_ENV_ALL_DELTA;
+    t.stale = (dirty && !progress) ? 1 : 0;               // ProgressRewardEnv._get_reward reads bucket xpos every step
     if (progress) {
       double gc = 0.0, bc = 0.0;
       for (int a = 0; a < NA; ++a) {
@@ -362,7 +387,7 @@ FM_HD void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* rewa
     if (reward) reward[env] = t.reward;
     if (terminated) terminated[env] = (unsigned char)t.terminated;
     if (scores) { scores[2 * env] = t.score[0]; scores[2 * env + 1] = t.score[1]; }
-    if (flags) flags[env] = (unsigned char)((t.out_of_reach ? 1 : 0) | (t.force_term ? 2 : 0) | ((S[w].flags & 15) << 2));
+    if (flags) flags[env] = (unsigned char)((t.out_of_reach ? 1 : 0) | (t.force_term ? 2 : 0) | ((S[w].flags & 15) << 2) | (t.index_err ? 64 : 0));
     if (ep_info) { ep_info[4 * env] = t.ep_ret; ep_info[4 * env + 1] = (float)t.ep_len; ep_info[4 * env + 2] = (float)t.score[0]; ep_info[4 * env + 3] = (float)t.score[1]; }
     int fl = S[w].flags;
     if (fl) st.i[(size_t)L::I_FLAGS * N + env] |= fl;
@@ -406,8 +431,8 @@ FM_HD void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
     else if (fidx < L::F_CTRL_T) v = (&s.arm_v[0][0])[fidx - L::F_ARM_V];
     else if (fidx < L::F_ACC_WS) v = s.ctrl_target[fidx - L::F_CTRL_T];
     else if (fidx < L::F_PRE_Q) v = s.belt_S;
-    else if (fidx < L::F_PRE_V) { v = (&s.cube_q[0][0])[fidx - L::F_PRE_Q]; wr = TS[e].done_prev != 0; }   // after a reset the model is in sync
-    else if (fidx < L::F_LAST_GD) { v = (&s.cube_v[0][0])[fidx - L::F_PRE_V]; wr = TS[e].done_prev != 0; }
+    else if (fidx < L::F_PRE_V) { v = (&s.cube_q[0][0])[fidx - L::F_PRE_Q]; wr = TS[e].done_prev != 0 || !TS[e].stale; }   // after a reset / a forward the model is in sync
+    else if (fidx < L::F_LAST_GD) { v = (&s.cube_v[0][0])[fidx - L::F_PRE_V]; wr = TS[e].done_prev != 0 || !TS[e].stale; }
     else if (fidx < L::F_LAST_BD) v = TS[e].last_gd[fidx - L::F_LAST_GD];
     else if (fidx < L::F_IK_ACT) v = TS[e].last_bd[fidx - L::F_LAST_BD];
     else if (fidx >= L::F_IK_LAST_CTRL && fidx < L::F_IK_MOVE_START) {   // IKPolicy.reset -> idle_ctrl (ik_policy.py:120-127)
@@ -417,6 +442,8 @@ FM_HD void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
     else if (fidx >= L::F_SITE && fidx < L::F_EP_RET) v = (&TS[e].site[0][0])[fidx - L::F_SITE];
     else if (fidx == L::F_EP_RET) v = TS[e].ep_ret;
     else if (fidx >= L::F_PREV_F && fidx < L::F_PREV_AF) wr = false;
+    else if (fidx >= L::F_ARM_QLO) v = s.arm_qlo(0)[fidx - L::F_ARM_QLO];
+    else if (fidx >= L::F_CUBE_QLO) v = (&s.cube_qlo[0][0])[fidx - L::F_CUBE_QLO];
     else if (fidx >= L::F_PREV_AF) v = (&s.prev_arow_f[0][0])[fidx - L::F_PREV_AF];
     else wr = false;
     if (wr) st.f[(size_t)fidx * N + env] = v;

