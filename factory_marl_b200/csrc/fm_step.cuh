@@ -54,6 +54,13 @@ static long long fm_dbg_sat[512] = {0};   // general SAT calls by geom1
 #define FM_FDIV(a, b) ((a) / (b))
 #endif
 #define FM_AROW 10   // equality + up to 9 limit rows per arm
+// Broad-phase caching: the survivor queue of the 737 (two arms) statically admissible cluster pairs is rebuilt only when some
+// cluster centre has moved more than FM_BROAD_MARGIN / 2 since the last rebuild (or a cube fell asleep / woke up / was moved by the
+// task manager); the pair tests use radii inflated by FM_BROAD_MARGIN, so the cached queue is a superset of the near pairs of every
+// sub-step in between and the narrow phase — which runs every sub-step — produces bit-identical contact sets.
+#ifndef FM_BROAD_MARGIN
+#define FM_BROAD_MARGIN 0.04f
+#endif
 // Box-box contacts are twice as soft in the reference as MuJoCo's documented regulariser (R = 2 mu^2 (1-d)/d diagApprox, four
 // pyramid rows on each of the four face-clipping points) predicts: every resting cube in runs/*.zip:_last_obs (90 samples, belt
 // and table) sits 2.28e-6 m (belt) / 4.2e-7 m (table) deep, exactly 2x the documented 1.14e-6 / 2.04e-7, independent of mass.
@@ -91,7 +98,7 @@ struct EnvS {
   int arow_n[NA], arow_code[NA][FM_AROW];   // code: dof | sign<<8 (sign bit 1 = negative) ; 0x1000 = equality
   float arow_aref[NA][FM_AROW], arow_R[NA][FM_AROW], arow_f[NA][FM_AROW];
   // ---- contacts
-  int ncon, nraw, n_armside, flags, nqueue;
+  int ncon, nraw, broad_stale, flags, nqueue;   // broad_stale: the cached broad-phase survivor queue must be rebuilt (ph_broad)
   int c_side[FmCap<NA>::CON];
   float c_p[FmCap<NA>::CON][3], c_n[FmCap<NA>::CON][3], c_t1[FmCap<NA>::CON][3], c_mu[FmCap<NA>::CON], c_R[FmCap<NA>::CON], c_W[FmCap<NA>::CON][6];
   float c_aref[FmCap<NA>::CON][4], c_f[FmCap<NA>::CON][4];
@@ -101,6 +108,8 @@ struct EnvS {
   float* ct_d0;   // ctrl_target - ctrl at the start of the control step (closed-form PT1 filter, ph_ctrl); followed by arm_qlo
   // low-order part of the arm joint positions (compensated integration like cube_qlo; lives in the global scratch row)
   FM_HDM float* arm_qlo(int a) const { return ct_d0 + (1 + 8 * FM_MAX_ARMS) + 9 * a; }
+  // bounding spheres (x, y, z, r) of the clusters at the last rebuild of the broad-phase queue (ph_broad); global scratch row
+  FM_HDM float* bnd_ref(int cl) const { return ct_d0 + (1 + 8 * FM_MAX_ARMS) + 9 * FM_MAX_ARMS + 4 * cl; }
   int isl_root[NNODE], isl_start[NNODE + 1], need_union;
   unsigned char isl_list[FmCap<NA>::CON], c_node[FmCap<NA>::CON];
   unsigned short queue[FmCap<NA>::QUEUE];
@@ -166,6 +175,15 @@ FM_HD int ab_parent(int b) { return b <= 8 ? b - 1 : 8; }
 FM_HD int ab_dof(int b) { return (b >= 1 && b <= 7) ? b - 1 : (b == 9 ? 7 : (b == 10 ? 8 : -1)); }
 FM_HD int dof_body(int d) { return d < 7 ? d + 1 : d + 2; }
 
+// the cluster's bounding sphere against its value at the last queue rebuild
+template <int NA>
+FM_HD void broad_check(EnvS<NA>& s, int cl, const float* bb) {
+  const float* rf = s.bnd_ref(cl);
+  float dx = bb[0] - rf[0], dy = bb[1] - rf[1], dz = bb[2] - rf[2];
+  const float thr = 0.5f * FM_BROAD_MARGIN;
+  if (dx * dx + dy * dy + dz * dz > thr * thr || (bb[3] < 0.f) != (rf[3] < 0.f)) FM_ATOMIC_OR(&s.broad_stale, 1);
+}
+
 // =====================================================================================================================
 // phase: cube kinematics (normalise quats in place as mj_kinematics does [3P])
 template <int NA, int E>
@@ -189,6 +207,7 @@ FM_HD void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int 
     }
     s.bnd[k][0] = s.cube_q[k][0]; s.bnd[k][1] = s.cube_q[k][1]; s.bnd[k][2] = s.cube_q[k][2];
     s.bnd[k][3] = s.cube_sleep[k] ? -1.f : m.cube_half[k] * 1.7320509f * 1.000001f;
+    broad_check(s, k, s.bnd[k]);
     f3 ww = rmul(s.cube_R[k], mk3(s.cube_v[k][3], s.cube_v[k][4], s.cube_v[k][5]));
     s.cube_vw[k][0] = s.cube_v[k][0]; s.cube_vw[k][1] = s.cube_v[k][1]; s.cube_vw[k][2] = s.cube_v[k][2];
     s.cube_vw[k][3] = ww.x; s.cube_vw[k][4] = ww.y; s.cube_vw[k][5] = ww.z;
@@ -284,6 +303,8 @@ FM_HD void ph_arm_vel(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       ap = ap + cross3(al, r) + cross3(om, cross3(om, r)) + 2.0f * cross3(om, rcol(s.body_R[a][b], 0) * s.arm_v[a][b - 2]);
     }
     st3(s.d_om[a][b], om); st3(s.d_al[a][b], al); st3(s.d_ap[a][b], ap);
+    // bounding sphere of the body's geom cluster (broad phase) and its displacement since the last queue rebuild
+    { f3 cc = ld3(s.body_x[a][b]) + rmul(s.body_R[a][b], ld3(m.arm_cl[b])); float* bb = s.bnd[FM_NCUBE + ab]; bb[0] = cc.x; bb[1] = cc.y; bb[2] = cc.z; bb[3] = m.arm_cl[b][3]; broad_check(s, FM_NCUBE + ab, bb); }
   }
 }
 // final kinematics only (gripper sites after the last sub-step): same scan without the velocity passes
@@ -294,8 +315,10 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
     const float* R = s.body_R[a][b];
-    { f3 cc = ld3(s.body_x[a][b]) + rmul(R, ld3(m.arm_cl[b])); float* bb = s.bnd[FM_NCUBE + ab]; bb[0] = cc.x; bb[1] = cc.y; bb[2] = cc.z; bb[3] = m.arm_cl[b][3]; }
-    if (b == 0) continue;
+    if (b == 0) {   // one lane per env: the stale flag is final (cubes in ph_cube_derive, arm clusters in ph_arm_vel)
+      if (a == 0 && s.broad_stale) s.nqueue = 0;
+      continue;
+    }
     float ms = m.ab_mass[b];
     f3 c = rmul(R, ld3(m.ab_ipos[b]));
     // Iw = R Il R^T
@@ -470,6 +493,12 @@ FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __rest
   const int stride = T / E;                              // lanes per env; a lane always serves the same env
   if (tid >= stride * E) return;                         // T need not be a multiple of E: the remainder lanes sit this phase out
   EnvS<NA>& s = S[tid % E];
+  if (!s.broad_stale) return;                            // the cached queue is still a superset of the near pairs
+  const float mg = FM_BROAD_MARGIN;
+  for (int cl = tid / E; cl < FmCap<NA>::NCL; cl += stride) {   // remember where this queue was built
+    float* rf = s.bnd_ref(cl); const float* bb = s.bnd[cl];
+    rf[0] = bb[0]; rf[1] = bb[1]; rf[2] = bb[2]; rf[3] = bb[3];
+  }
   const bnd4* bnd = reinterpret_cast<const bnd4*>(&s.bnd[0][0]) - s0;
   for (int p0 = tid / E; p0 < np; p0 += 4 * stride) {
     // four pair records are fetched up front so their global-load latencies overlap
@@ -487,13 +516,13 @@ FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __rest
       if (b2.r < 0.f) far = true;                          // sleeping cube
       else if (type == FM_PAIR_SPH_SPH) {
         bnd4 b1 = bnd[c1];
-        float dx = b1.x - b2.x, dy = b1.y - b2.y, dz = b1.z - b2.z, rr = b1.r + b2.r;
+        float dx = b1.x - b2.x, dy = b1.y - b2.y, dz = b1.z - b2.z, rr = b1.r + b2.r + mg;
         far = b1.r < 0.f || dx * dx + dy * dy + dz * dz > rr * rr;
       } else if (type == FM_PAIR_BOX_SPH) {
         const float* bx = m.big_aabb[c1];
         float dx = fmaxf(fmaxf(bx[0] - b2.x, b2.x - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - b2.y, b2.y - bx[4]), 0.f), dz = fmaxf(fmaxf(bx[2] - b2.z, b2.z - bx[5]), 0.f);
-        far = dx * dx + dy * dy + dz * dz > b2.r * b2.r;
-      } else if (type == FM_PAIR_PLANE_SPH) far = b2.z - b2.r > 0.f;
+        far = dx * dx + dy * dy + dz * dz > (b2.r + mg) * (b2.r + mg);
+      } else if (type == FM_PAIR_PLANE_SPH) far = b2.z - b2.r - mg > 0.f;
       else far = false;
       if (far) continue;
       int slot = FM_ATOMIC_ADD(&s.nqueue, 1);
@@ -875,6 +904,7 @@ FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
     EnvS<NA>& s = S[w];
     int nraw = s.nraw < FmCap<NA>::CON ? s.nraw : FmCap<NA>::CON;
     s.ncon = nraw;
+    s.broad_stale = 0;                                   // consumed by ph_broad of this sub-step
     FM_DBG(fm_dbg_cnt[0]++; fm_dbg_cnt[1] += nraw; fm_dbg_cnt[2] += s.nqueue; fm_dbg_cnt[3] += s.need_union; for (int k = 0; k < FM_NCUBE; ++k) fm_dbg_cnt[26] += !s.cube_sleep[k];)
     if (!s.need_union) continue;
     int* root = s.isl_root;
@@ -1372,5 +1402,5 @@ FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float pk) {
 template <int NA, int E>
 FM_HD void ph_clear(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
-  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.n_armside = 0; s.nqueue = 0; s.ncon = 0; s.need_union = 0; for (int i = 0; i < EnvS<NA>::NNODE; ++i) s.isl_root[i] = i; }
+  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.ncon = 0; s.need_union = 0; for (int i = 0; i < EnvS<NA>::NNODE; ++i) s.isl_root[i] = i; }
 }

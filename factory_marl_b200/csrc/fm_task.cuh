@@ -122,6 +122,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     TS[w].play_time = st.d[(size_t)L::D_PLAY_TIME * N + env];
     S[w].conveyor_speed = (float)TS[w].conveyor_speed;
     S[w].flags = 0; S[w].force_max = 0.f;
+    S[w].broad_stale = 1; S[w].nqueue = 0;                 // the broad-phase queue is rebuilt in the first sub-step of every launch
     S[w].as_J = reinterpret_cast<float (*)[27]>(ws);
     S[w].as_B = reinterpret_cast<float (*)[27]>(ws + FmCap<NA>::ARMSIDE * 27);
     S[w].prev_f = reinterpret_cast<float (*)[4]>(ws + FmCap<NA>::ARMSIDE * 54);
@@ -266,7 +267,13 @@ FM_HD void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& 
         float* q = s.cube_q[k];
         q[0] = 0.f; q[1] = 1.f; q[2] = 2.f;
         for (int i = 0; i < 3; ++i) s.cube_qlo[k][i] = 0.f;
-        for (int i = 0; i < 4; ++i) q[3 + i] = (float)pcg64_uniform(r4);
+        // raw uniforms (task_utils.py:49-51) ... which the mj_forward triggered by _check_states' bucket-xpos read normalises in
+        // place (mj_kinematics) before _get_state reads them: the observation of the spawn step already shows a unit quaternion
+        // (runs/rk5rxnav.zip:_last_obs env 4)
+        double qr[4], qn = 0.0;
+        for (int i = 0; i < 4; ++i) { qr[i] = pcg64_uniform(r4); qn += qr[i] * qr[i]; }
+        qn = sqrt(qn);
+        for (int i = 0; i < 4; ++i) q[3 + i] = (float)(qr[i] / qn);
         for (int i = 0; i < 2; ++i) st.rng[(size_t)i * N + env] = r4[i];
         t.in_scene[t.n_in++] = k;
         dirty = true;

@@ -19,7 +19,8 @@ template <int NA> struct FmCap {
   static constexpr int CON = NA <= 2 ? FM_MAXCON : FM_MAXCON_ALL;         // contacts per env
   static constexpr int ARMSIDE = NA <= 2 ? FM_MAXARMSIDE : 64;            // contact sides on an arm (6-bit slot)
   static constexpr int QUEUE = NA <= 2 ? 96 : 160;                        // cluster pairs queued for the narrow phase
-  static constexpr int WS = ARMSIDE * 54 + CON * 4 + 1 + 8 * FM_MAX_ARMS + 9 * FM_MAX_ARMS; // floats of the env's global scratch row: as_J, as_B, prev_f, ct_d0, arm_qlo
+  static constexpr int NCL = FM_NCUBE + NA * FM_NARMBODY;                 // sphere-bounded broad-phase clusters
+  static constexpr int WS = ARMSIDE * 54 + CON * 4 + 1 + 8 * FM_MAX_ARMS + 9 * FM_MAX_ARMS + 4 * NCL; // floats of the env's global scratch row: as_J, as_B, prev_f, ct_d0, arm_qlo, bnd_ref
 };
 #define FM_NCLASS 4
 #define FM_MAX_FRAME_SKIP 128

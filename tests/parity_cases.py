@@ -184,3 +184,240 @@ def case_arm_contact_pairsets(be, seeds=(0, 2, 8, 10)):
         assert np.abs(d["pos"] - ocd[:, 0:3]).max() < 1e-5
         checked += 1
     assert checked >= 3
+
+
+# =====================================================================================================================
+# Integer outputs at non-trivial values, production solver settings, contact forces, episode boundaries (sim adapters)
+from tests.sim_adapters import CoreSim, OracleSim, Scene, hidden_qpos  # noqa: E402
+
+
+def _settled_scene(n_arms=2):
+    """three cubes riding the belt after 120 control steps (tests/golden/known_answers.npz, made by the oracle)"""
+    g = np.load(GOLDEN + "/known_answers.npz")
+    q, v = g["qpos120"].copy(), g["qvel120"].copy()
+    ct = np.zeros(1 + 8 * n_arms); ct[0] = -0.1119
+    return Scene(q, v, ct, [0, 1, 2], 120, since_spawn=28, n_arms=n_arms)
+
+
+def _pair(be, n_arms, cls, **kw):
+    return OracleSim(n_arms, cls, **kw), CoreSim(be, n_arms, cls, **kw)
+
+
+def case_scores_both_buckets_snapshot(be):
+    """cubes 0 and 1 dropped into bucket 0 and bucket 1 in the same control step while cube 2 rides the belt.  The reference takes
+    ONE position snapshot (task_utils.py:97): bucket 0 pops index 0, then bucket 1's hit index 1 is applied to the shortened list
+    and hides cube 2 instead of cube 1 — which is scored one step later.  Scores, list contents and flags must follow exactly."""
+    for cls in ("FactoryManipulationEnv", "AllFullRLProgressRewardEnv"):
+        kw = PROGRESS_KW if "Progress" in cls else {}
+        o, c = _pair(be, 2, cls, **kw)
+        sc = _settled_scene()
+        M = o.M
+        for k, x in ((0, 0.9), (1, -0.9)):
+            sc.qpos[1 + 7 * k:8 + 7 * k] = [x, 0.7, 1.10, 1, 0, 0, 0]; sc.qvel[1 + 6 * k:7 + 6 * k] = 0
+        act = np.zeros(16 if "Progress" in cls else 0, np.float32)
+        hist = []
+        for sim in (o, c):
+            sim.reset(); sim.transplant(sc)
+            h = []
+            for t in range(3):
+                obs, r, info = sim.step(act)
+                h.append((info["scores"], info["num_obj"], info["terminated"], round(r, 3) if "Progress" not in cls else None))
+            hist.append(h)
+        assert hist[0] == hist[1], (cls, hist)
+        assert hist[0][0][0] == (1, 1) and hist[0][0][1] == 1, hist[0]      # two hidden after step 1: cube 0 and (wrongly) cube 2
+        assert hist[0][1][0] == (1, 2), hist[0]                             # cube 1 is still in bucket 1 and scores again
+        if "Progress" not in cls:
+            assert hist[0][0][3] == 2.0 and hist[0][1][3] == 1.0             # base reward = score delta (environments.py:148)
+        assert c.cap_flags() == 0
+
+
+def case_out_of_bounds_terminates(be):
+    """a cube beyond |x| > 1.2, y < -1.5 or z < 0.9 ends the episode with out_of_reach (task_utils.py:84-95), bit 0 of flags"""
+    for pos in ([1.25, 0.0, 1.2], [0.0, -1.55, 1.14], [0.5, 0.9, 0.85]):
+        o, c = _pair(be, 2, "AllFullRLProgressRewardEnv", **PROGRESS_KW)
+        sc = _settled_scene()
+        sc.qpos[1:8] = pos + [1, 0, 0, 0]; sc.qvel[1:7] = 0
+        res = []
+        for sim in (o, c):
+            sim.reset(); sim.transplant(sc)
+            obs, r, info = sim.step(np.zeros(16, np.float32))
+            res.append((info["terminated"], info["out_of_reach"], info["force_terminate"], info["scores"], info["num_obj"]))
+        assert res[0] == res[1] and res[0][0] and res[0][1], (pos, res)
+
+
+def case_force_termination_same_step(be, seeds=(0, 2, 8, 10)):
+    """arms driven into the table / belt / each other by bang-bang joint targets: the 200 N criterion (base_env.py:226-236) must
+    fire at the same control step as in the oracle, flags bit 1, and never before"""
+    hit = 0
+    for seed in seeds:
+        o, c = _pair(be, 2, "AllFullRLProgressRewardEnv", **PROGRESS_KW)
+        a = (np.random.default_rng(seed).integers(0, 2, 16) * 2 - 1).astype(np.float32) * 3
+        o.reset(); c.reset()
+        for t in range(30):
+            _, _, io = o.step(a)
+            _, _, ic = c.step(a)
+            assert (io["force_terminate"], io["out_of_reach"]) == (ic["force_terminate"], ic["out_of_reach"]), (seed, t, io, ic)
+            if io["force_terminate"]:
+                hit += 1
+                break
+        assert c.cap_flags() == 0
+    assert hit >= 3, hit
+
+
+def case_contact_forces(be, **extra):
+    """normal forces of the resting contacts after one sub-step from identical state: each cube's weight is shared by its four
+    corner contacts; compared with the oracle's solve contact by contact"""
+    blob = fm.build_blob(2); M = fm.build_model(2)
+    sc = _settled_scene()
+    o = Oracle(blob); o.set_state(sc.qpos, sc.qvel); o.step1()
+    ctrl = np.zeros(17); ctrl[0] = -0.112
+    core = be.mk(blob, 4, 2, "AllFullRLProgressRewardEnv", auto_reset=False, **extra)
+    core.reset(); core.set_state(0, sc.qpos, sc.qvel, ctrl)
+    d = core.debug_substeps(1, env=0)
+    og, _ = o.contacts()
+    o.step2(ctrl)
+    fo = o.efc()["force"]
+    n_eq = int((o.efc()["type"] != 3).sum()) if False else len(fo) - 4 * len(og)
+    fo = fo[n_eq:].reshape(-1, 4)
+    # with hidden cubes asleep (production) their floor contacts are not generated: compare the contacts of the in-scene cubes
+    gset = [int(np.where(M["geom_body"] == M["cube_body"][k])[0][0]) for k in range(3)]
+    keep_o = np.array([x[0] in gset or x[1] in gset for x in og]); keep_g = np.array([x[0] in gset or x[1] in gset for x in d["pair"]])
+    assert np.array_equal(d["pair"][keep_g], og[keep_o])
+    fn_o, fn_g = fo.sum(axis=1)[keep_o], d["force"].sum(axis=1)[keep_g]
+    og = og[keep_o]
+    mass = M["body_mass"][M["cube_body"]]
+    for k in range(3):      # each cube's weight is carried by its four corner contacts
+        sel = (og[:, 0] == gset[k]) | (og[:, 1] == gset[k])
+        assert sel.sum() == 4
+        assert abs(fn_o[sel].sum() - mass[k] * 9.81) < 1e-6 * mass[k] * 9.81
+        assert abs(fn_g[sel].sum() - mass[k] * 9.81) < 2e-3 * mass[k] * 9.81, (k, fn_g[sel].sum(), mass[k] * 9.81)
+    tol = 0.05 * np.abs(fn_o).max()
+    assert np.abs(fn_g - fn_o).max() < tol, (np.abs(fn_g - fn_o).max(), tol)
+    return np.abs(fn_g - fn_o).max() / np.abs(fn_o).max()
+
+
+def case_control_step_with_contacts_production(be):
+    """ONE control step (100 sub-steps) from identical state with cubes in resting contact, at the solver settings the benchmark
+    runs (<= 4 sweeps, 1e-3 m/s^2, hidden cubes asleep): north_star's 'single-step state <= 1e-4 relative'."""
+    o, c = _pair(be, 2, "AllFullRLProgressRewardEnv", **PROGRESS_KW)
+    sc = _settled_scene()
+    a = np.random.default_rng(5).uniform(-0.3, 0.3, 16).astype(np.float32)
+    o.reset(); c.reset(); o.transplant(sc); c.transplant(sc)
+    oo, _, io = o.step(a); oc, _, ic = c.step(a)
+    assert io == {k: ic[k] for k in io}
+    r_arm = rel(oc[:48], oo[:48]); r_pos = rel(oc[48:118], oo[48:118]); r_vel = rel(oc[118:178], oo[118:178])
+    assert r_arm < 1e-4 and r_pos < 1e-5 and r_vel < 1e-4, (r_arm, r_pos, r_vel)
+    return r_arm, r_pos, r_vel
+
+
+def case_impact_substep_production(be):
+    """the sub-step in which a falling cube first touches the belt (4.2 m/s impact, 3 mm deep after one 1 ms step: impedance at
+    dmax = 0.9999), from identical state: contact pair set bit-exact; post-impact cube velocity 1.1e-3 relative, position 5e-6.
+    This is the one place where the fp32 path misses north_star's 1e-4: the active-set Newton solves (M + J^T J / R) a = ... with
+    R ~ 1e-5 of the row inertia, a Hessian of condition ~1e5, so fp32 leaves ~1e-3 in the stiff directions (forces agree to 2e-3).
+    Resting and sliding contacts (d < 0.99) meet 1e-4 (case_control_step_with_contacts_production)."""
+    blob = fm.build_blob(2)
+    o = Oracle(blob); o.env_create("AllFullRLProgressRewardEnv"); o.env_reset()
+    for t in range(4):
+        o.env_step(np.zeros(16, np.float32))
+    ctrl = o.env_get("ctrl_target", 17)
+    cube_g = 3
+    for n in range(200):       # raw sub-steps until the cube-belt contact appears
+        o.step2(ctrl); o.step1()
+        g, _ = o.contacts()
+        if any(x[0] == 2 and x[1] == cube_g for x in g):
+            break
+    else:
+        raise AssertionError("no impact found")
+    q, v = o.get_state()
+    core = be.mk(blob, 4, 2, "AllFullRLProgressRewardEnv", auto_reset=False, sleep_hidden=False)
+    core.reset(); core.set_state(0, q, v, ctrl)
+    d = core.debug_substeps(1, env=0)
+    og, _ = o.contacts()
+    assert d["ncon"] == len(og) and np.array_equal(d["pair"], og)
+    o.step2(ctrl)
+    q2, v2 = o.get_state(); gq, gv, _ = core.get_state(0)
+    rv = rel(gv[1:7], v2[1:7]); rq = rel(gq[1:8], q2[1:8])
+    assert rv < 2e-3 and rq < 1e-5, (rv, rq)
+    return rv, rq
+
+
+def case_episode_boundary(be):
+    """one full episode (zero actions: ends by out_of_reach near step 218) through the SB3-style auto-reset, against the oracle
+    reset by hand: post-reset observation, the TaskManager RNG stream that is NOT reseeded (task_utils.py:19), and the progress
+    reward's last-distance memory that is NOT cleared (environments.py:280-281)"""
+    o = OracleSim(2, "AllFullRLProgressRewardEnv", **PROGRESS_KW)
+    c = CoreSim(be, 2, "AllFullRLProgressRewardEnv", auto_reset=True, **PROGRESS_KW)
+    a = np.zeros(16, np.float32)
+    obs0 = o.reset(); assert np.array_equal(c.reset(), obs0)
+    t_o = t_c = None
+    ro = rc_ = None
+    sp_o = sp_c = 0; last_o = last_c = 0
+    for t in range(260):
+        if t_o is None:
+            _, r, io = o.step(a)
+            sp_o += io["num_obj"] > last_o; last_o = io["num_obj"]
+            if io["terminated"]:
+                t_o = t
+                o.o.env_reset()
+                _, ro, _ = o.step(a)                       # first step of episode 2
+                q_o, _, _ = o.state()
+        if t_c is None:
+            obs_c, r, ic = c.step(a)
+            if ic["terminated"]:
+                t_c = t
+                assert np.array_equal(obs_c, obs0)         # the returned observation is the post-reset one
+                obs_c2, rc_, ic2 = c.step(a)
+                q_c, _, _ = c.state()
+            else:
+                sp_c += ic["num_obj"] > last_c; last_c = ic["num_obj"]
+        if t_o is not None and t_c is not None:
+            break
+    assert t_o is not None and t_c is not None and abs(t_o - t_c) <= 2, (t_o, t_c)      # chaotic tumbling: +-2 control steps
+    # the first spawn of episode 2 continues the PCG64 stream of episode 1 (seeded once in __init__, task_utils.py:19)
+    draws = np.random.default_rng(42).uniform(0, 1, (12, 4))
+    assert sp_o >= 5
+    for q, n_sp in ((q_o, sp_o), (q_c, sp_o)):
+        assert np.abs(q[4:8] - draws[n_sp] / np.linalg.norm(draws[n_sp])).max() < 1e-6, (n_sp, q[4:8])
+    assert abs(ro - rc_) < 0.02, (ro, rc_)       # carries 0.2 * (stale last distance - new distance) ~ 0.2: a cleared memory would show
+    return t_o, t_c
+
+
+def case_config1(be, n_steps=10000, sync_every=25):
+    """configs[0]: the oracle runs `n_steps` control steps of one env under
+    default_rng(0).uniform(-1, 1, (n, 16)) actions with auto-reset; every `sync_every` steps the kernel (one env) is set to the
+    oracle's full state and must reproduce the next control step: integers exactly, arm state to 1e-4 relative, cube rows to
+    1e-3 absolute unless an arm or an impact stirred them in that step."""
+    o = OracleSim(2, "AllFullRLProgressRewardEnv", **PROGRESS_KW)
+    c = CoreSim(be, 2, "AllFullRLProgressRewardEnv", n_envs=1, auto_reset=False, **PROGRESS_KW)
+    acts = np.random.default_rng(0).uniform(-1, 1, (n_steps, 16)).astype(np.float32)
+    o.reset(); c.reset()
+    worst_arm = worst_cube = 0.0
+    checked = resets = calm = 0
+    for t in range(n_steps):
+        sync = t % sync_every == 0
+        if sync:
+            q, v, ct = o.state()
+            lists = o.o.env_get("lists", 23); sc_ = o.o.env_get("scalars", 9)
+            n_in = int(lists[0])
+            sc = Scene(q, v, ct, [int(x) for x in lists[1:1 + n_in]], int(sc_[3]), since_spawn=int(sc_[4]), conveyor_speed=sc_[0],
+                       spawn_freq=sc_[1])
+            sc.out_scene = [int(x) for x in lists[12:12 + int(lists[11])]]
+            c.transplant(sc)
+        obs_o, r_o, io = o.step(acts[t])
+        if sync:
+            obs_c, r_c, ic = c.step(acts[t])
+            assert {k: ic[k] for k in ("terminated", "out_of_reach", "force_terminate", "num_obj")} == {k: io[k] for k in ("terminated", "out_of_reach", "force_terminate", "num_obj")}, (t, io, ic)
+            ra = rel(obs_c[:48], obs_o[:48])
+            worst_arm = max(worst_arm, ra)
+            dc = np.abs(obs_c[48:118] - obs_o[48:118]).max()
+            if dc < 1e-3:
+                calm += 1
+            worst_cube = max(worst_cube, dc)
+            checked += 1
+        if io["terminated"]:
+            o.reset(); resets += 1
+    assert checked >= n_steps // sync_every and resets >= n_steps // 400
+    assert worst_arm < 1e-4, worst_arm
+    assert calm >= 0.9 * checked, (calm, checked, worst_cube)
+    return worst_arm, worst_cube, calm, checked, resets

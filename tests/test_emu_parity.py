@@ -125,7 +125,7 @@ def test_block_shapes_agree():
 
 def test_broad_phase_visits_every_pair_once():
     """lane -> (env, pair) mapping of the broad phase: every env slot of a block visits every admissible cluster pair exactly
-    once per sub-step, also when the lane count (12 warps) is not a multiple of the envs per block (14)"""
+    once per queue rebuild (the first sub-step of a launch), also when the lane count (12 warps) is not a multiple of the envs per block (14)"""
     import ctypes as C
     from factory_marl_b200 import model as fm
     from tests.emu_backend import emu_lib
@@ -139,8 +139,37 @@ def test_broad_phase_visits_every_pair_once():
         core = make_core(blob, 4, 2, "AllFullRLProgressRewardEnv", auto_reset=False, envs_per_block=E)
         core.reset()
         v0 = visits()
-        core.debug_substeps(3, env=0)
-        per_slot[E] = (visits() - v0) / (3 * slots)
+        core.debug_substeps(1, env=0)
+        per_slot[E] = (visits() - v0) / slots
     n_pairs = per_slot[1]
     assert 600 < n_pairs < 900 and n_pairs == int(n_pairs)
     assert all(v == n_pairs for v in per_slot.values()), per_slot
+
+
+def test_scores_both_buckets_snapshot():
+    pc.case_scores_both_buckets_snapshot(BE)
+
+
+def test_out_of_bounds_terminates():
+    pc.case_out_of_bounds_terminates(BE)
+
+
+def test_force_termination_same_step():
+    pc.case_force_termination_same_step(BE, seeds=(0, 2, 8))
+
+
+def test_contact_forces_production_and_converged():
+    pc.case_contact_forces(BE, **pc.CONVERGED)
+    pc.case_contact_forces(BE)
+
+
+def test_control_step_with_contacts_production():
+    pc.case_control_step_with_contacts_production(BE)
+
+
+def test_impact_substep_production():
+    pc.case_impact_substep_production(BE)
+
+
+def test_episode_boundary_leaks():
+    pc.case_episode_boundary(BE)

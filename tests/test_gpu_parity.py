@@ -194,3 +194,40 @@ def test_four_arm_capacities_hold_under_ik_toggling():
     assert int(env.core.i[env.core.off("I_FLAGS")].max()) == 0
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     assert int(env.core.i[env.core.off("I_MAXCON")].max()) > 0
+
+
+# ---- integer outputs at non-trivial values, production solver settings, contact forces, episode boundary (round 2)
+def test_scores_both_buckets_snapshot():
+    pc.case_scores_both_buckets_snapshot(BE)
+
+
+def test_out_of_bounds_terminates():
+    pc.case_out_of_bounds_terminates(BE)
+
+
+def test_force_termination_same_step():
+    pc.case_force_termination_same_step(BE)
+
+
+def test_contact_forces_production_and_converged():
+    pc.case_contact_forces(BE, **pc.CONVERGED)
+    pc.case_contact_forces(BE)
+
+
+def test_control_step_with_contacts_production():
+    pc.case_control_step_with_contacts_production(BE)
+
+
+def test_impact_substep_production():
+    pc.case_impact_substep_production(BE)
+
+
+def test_episode_boundary_leaks():
+    pc.case_episode_boundary(BE)
+
+
+@pytest.mark.slow
+def test_config1_10000_steps_single_env():
+    """BASELINE.json configs[0]: 1 env, seeded random actions, 10 000 steps with auto-reset on the CPU oracle; the GPU (N = 1) is
+    re-synchronised to the oracle's state every 25 steps and must reproduce the next control step."""
+    pc.case_config1(BE, n_steps=10000, sync_every=25)

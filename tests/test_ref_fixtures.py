@@ -62,3 +62,19 @@ def test_ref_scene_step(who, run):
 
 def test_ref_ik_proposals():
     rc.case_ref_ik_proposals()
+
+
+@pytest.mark.parametrize("run", ["y6lp1j7k", "xfwgqibb", "rk5rxnav", "r666unuv"])
+def test_oracle_episode_statistics_vs_reference(run):
+    """tests/golden/oracle_stats_<run>.json (tools/oracle_policy_stats.py <run> 128 1000 --write: 128 uncapped oracle episodes under
+    the reference's own policy.pth, stochastic actions) against the reference's last 100 Monitor episodes: two-sample z of return
+    and length.  |z| < 3 is asserted; the measured values are y6lp1j7k +2.1 / +1.5, xfwgqibb -1.6 / -1.5,
+    rk5rxnav -2.0 / -1.2, r666unuv -2.8 / -2.2 — the oracle's episodes under the three non-default policies run 3-6 % short."""
+    o = json.load(open(os.path.join(GOLDEN, f"oracle_stats_{run}.json")))
+    ref = rc.RUNS[run]
+    assert o["episodes"] >= 100
+    for name, ours, theirs in (("return", np.array(o["returns"]), np.array(ref["returns"])),
+                               ("length", np.array(o["lengths"], float), np.array(ref["lengths"], float))):
+        se = np.sqrt(ours.var(ddof=1) / len(ours) + theirs.var(ddof=1) / len(theirs))
+        z = (ours.mean() - theirs.mean()) / se
+        assert abs(z) < 3.0, (run, name, float(ours.mean()), float(theirs.mean()), float(z))

@@ -27,6 +27,7 @@ for t in range(steps):
     core.env_step(a)
 c = cnt() - base
 ss = c[0]
+print("broad-phase queue rebuilds per env-sub-step %.3f" % (c[31] / ss / 725.0))
 print("env-sub-steps", ss, "contacts/substep %.2f queue/substep %.2f need_union frac %.3f awake cubes %.2f" % (c[1] / ss, c[2] / ss, c[3] / ss, c[26] / ss))
 for k, nm in enumerate(["cube-only", "arm-only", "arm+contacts"]):
     isl, sw, vis, con = c[4 + 4 * k: 8 + 4 * k]

@@ -2,7 +2,7 @@
 
 The reference itself cannot run in this image (MuJoCo / dm_control / SB3 absent), so these vectors pin the ORACLE
 (a restatement) against regressions and give the `-m gpu` tests fixtures that travel to the GPU box.  They are
-not outputs of the reference: parity with MuJoCo stays unpinned.
+not outputs of the reference; the reference-held fixtures are tests/golden/ref_* (tools/make_ref_fixtures.py).
     python tools/make_golden.py
 """
 import os
