@@ -40,7 +40,10 @@ FM_HD void fm_arm_kinematics(Run& run, EnvS<NA>* S, const FmDevModel& m, int T) 
 }
 
 // warps of the factorisation group / of the narrow-phase group when a block of TW warps splits (see fm_derive)
-FM_HDM constexpr int fm_split_a(int TW) { return TW >= 12 ? 8 : (TW >= 7 ? 5 : (TW >= 4 ? 3 : TW)); }
+#ifndef FM_SPLIT_WA12
+#define FM_SPLIT_WA12 8
+#endif
+FM_HDM constexpr int fm_split_a(int TW) { return TW >= 12 ? FM_SPLIT_WA12 : (TW >= 7 ? 5 : (TW >= 4 ? 3 : TW)); }
 
 template <int NA, int E, int TW, class Run>
 FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class, int sleep_hidden) {

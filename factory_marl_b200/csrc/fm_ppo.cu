@@ -385,6 +385,21 @@ static int mlp_backward(const fm_ppo_net* net, const fm_ppo_ws* ws, int which, i
   return gemm<64, true, true, EPI_ATOMIC_F32>(ws->x, Dp, ws->dh1[which], 128, G + net->w1[which], 128, Dp, 128, n, sk, nullptr, nullptr, 0, s);
 }
 
+#define FM_MON_WINDOW 100
+__global__ void monitor_kernel(const uint8_t* __restrict__ term, const float* __restrict__ ep, int n, int16_t* hist, int16_t* first,
+                               int32_t* count, float* ring, int32_t* ring_head) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || !term[e]) return;
+  const int c = count[e];
+  const int16_t s0 = (int16_t)ep[4 * e + 2], s1 = (int16_t)ep[4 * e + 3];
+  if (c == 0) { first[2 * e] = s0; first[2 * e + 1] = s1; }
+  int16_t* h = hist + ((size_t)e * FM_MON_WINDOW + c % FM_MON_WINDOW) * 2;
+  h[0] = s0; h[1] = s1;
+  count[e] = c + 1;
+  const int slot = atomicAdd(ring_head, 1) % FM_MON_WINDOW;
+  ring[2 * slot] = ep[4 * e]; ring[2 * slot + 1] = ep[4 * e + 1];
+}
+
 extern "C" {
 
 /* SB3 ActorCriticPolicy.forward over a batch of observations (collect_rollouts, learning.py:112): actions for the env
@@ -461,6 +476,16 @@ int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, floa
   adam_kernel<<<FM_ADAM_BLOCKS, 256, 0, s>>>(net->params, net->params_bf16, net->grads, net->adam_m, net->adam_v, net->n_params, lr, beta1, beta2, eps,
                                              max_grad_norm, grad_scale, step, norm2, stats);
   adam_count_kernel<<<1, 1, 0, s>>>(step, norm2, stats);
+  PPO_CUDA(cudaGetLastError());
+  return 0;
+}
+/* Monitor + ep_score_history + AdditionalMetricsCallback state (learning.py:53-72,98; environments.py:53,200-201), one launch per
+ * env step instead of a get_attr round trip over pipes: for every env that terminated in this step, its episode's scores go into
+ * the env's history ring (the callback looks at the last <= 100 episodes per env) and (return, length) into the ring of the last
+ * 100 episodes over all envs (SB3's ep_info_buffer, stats_window_size 100). */
+int fm_monitor_update(const uint8_t* terminated, const float* ep_info, int n, int16_t* hist, int16_t* first, int32_t* count,
+                      float* ring, int32_t* ring_head, void* stream) {
+  monitor_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(terminated, ep_info, n, hist, first, count, ring, ring_head);
   PPO_CUDA(cudaGetLastError());
   return 0;
 }

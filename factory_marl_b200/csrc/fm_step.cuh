@@ -316,7 +316,11 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
     const float* R = s.body_R[a][b];
     if (b == 0) {   // one lane per env: the stale flag is final (cubes in ph_cube_derive, arm clusters in ph_arm_vel)
+#ifdef FM_BROAD_ALWAYS
+      if (a == 0) s.nqueue = 0;
+#else
       if (a == 0 && s.broad_stale) s.nqueue = 0;
+#endif
       continue;
     }
     float ms = m.ab_mass[b];
@@ -493,7 +497,9 @@ FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __rest
   const int stride = T / E;                              // lanes per env; a lane always serves the same env
   if (tid >= stride * E) return;                         // T need not be a multiple of E: the remainder lanes sit this phase out
   EnvS<NA>& s = S[tid % E];
+#ifndef FM_BROAD_ALWAYS
   if (!s.broad_stale) return;                            // the cached queue is still a superset of the near pairs
+#endif
   const float mg = FM_BROAD_MARGIN;
   for (int cl = tid / E; cl < FmCap<NA>::NCL; cl += stride) {   // remember where this queue was built
     float* rf = s.bnd_ref(cl); const float* bb = s.bnd[cl];

@@ -18,10 +18,18 @@ def shard_seeds(base_seed: int, total_envs: int, rank: int, world: int):
     return list(range(base_seed + lo, base_seed + hi))
 
 
-def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
-    """sum all-reduce of the flat gradient, then divide by the world size (the clip must see the averaged gradient)."""
+def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
+    """THE collective of the path: one sum all-reduce of the flat fp32 gradient per optimiser step (NCCL over NVLink on the GPU
+    box, gloo in the CPU tests).  The division by the world size happens inside the clip + Adam kernel (`grad_scale`), because the
+    global-norm clip must see the averaged gradient (ppo.PPO.train)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    allreduce_sum_(flat)
+    if dist.is_initialized() and dist.get_world_size() > 1:
         flat.div_(dist.get_world_size())
     return flat
 

@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import lib as _lib
+from . import dist as _dist, lib as _lib
 
 
 class fm_ppo_net(C.Structure):
@@ -103,6 +103,7 @@ class PolicyValueNet:
     # ---- parameters
     def _alloc_ws(self, cap):
         cap = (cap + 63) // 64 * 64
+        self.ws_generation = getattr(self, "ws_generation", 0) + 1   # CUDA graphs captured over the old buffers are stale (PPO checks)
         d, H = self.dev, self.HID
         z = lambda *s, dt=torch.bfloat16: torch.zeros(s, dtype=dt, device=d)
         self._bufs = dict(x=z(cap, self.obs_pad), h1=[z(cap, H), z(cap, H)], h2=[z(cap, H), z(cap, H)],
@@ -123,9 +124,19 @@ class PolicyValueNet:
         o = self.off[(name, which)]
         return self.params[o:o + rows * cols].view(rows, cols)
 
-    def set_sb3_state_dict(self, sd):
+    def set_sb3_state_dict(self, sd, into=None):
         """Load an SB3 `policy.pth` state-dict (runs/*.zip): Linear weights are [out, in]; ours are [in(padded), out(padded)]."""
         H, D = self.HID, self.obs_dim
+        buf = self.params if into is None else into          # `into`: the Adam moment buffers share the parameter layout
+        saved, self.params = self.params, buf
+        try:
+            self._set_sb3(sd, H, D)
+        finally:
+            self.params = saved
+        if into is None:
+            self.sync_bf16()
+
+    def _set_sb3(self, sd, H, D):
         self.params.zero_()
         for which, pre in ((0, "mlp_extractor.policy_net"), (1, "mlp_extractor.value_net")):
             self._view("w1", which, self.obs_pad, H)[:D].copy_(sd[f"{pre}.0.weight"].t())
@@ -138,11 +149,18 @@ class PolicyValueNet:
         self._view("b3", 1, 1, 16)[0, :1].copy_(sd["value_net.bias"])
         if not self.discrete:
             self.params[self.off["log_std"]:self.off["log_std"] + self.act_dim].copy_(sd["log_std"])
-        self.sync_bf16()
 
-    def sb3_state_dict(self):
+    def sb3_state_dict(self, src=None):
         H, D = self.HID, self.obs_dim
+        if src is not None:                                   # same layout, another buffer (Adam moments)
+            saved, self.params = self.params, src
+            try:
+                return self.sb3_state_dict()
+            finally:
+                self.params = saved
         sd = {}
+        if not self.discrete:
+            sd["log_std"] = self.params[self.off["log_std"]:self.off["log_std"] + self.act_dim].clone().cpu()
         for which, pre in ((0, "mlp_extractor.policy_net"), (1, "mlp_extractor.value_net")):
             sd[f"{pre}.0.weight"] = self._view("w1", which, self.obs_pad, H)[:D].t().contiguous().cpu()
             sd[f"{pre}.0.bias"] = self._view("b1", which, 1, H)[0].clone().cpu()
@@ -152,8 +170,6 @@ class PolicyValueNet:
         sd["action_net.bias"] = self._view("b3", 0, 1, self.out_pad)[0, :self.n_out].clone().cpu()
         sd["value_net.weight"] = self._view("w3", 1, H, 16)[:, :1].t().contiguous().cpu()
         sd["value_net.bias"] = self._view("b3", 1, 1, 16)[0, :1].clone().cpu()
-        if not self.discrete:
-            sd["log_std"] = self.params[self.off["log_std"]:self.off["log_std"] + self.act_dim].clone().cpu()
         return sd
 
     def load_sb3_zip(self, path):
@@ -199,6 +215,15 @@ class PolicyValueNet:
         self.launches += 9 if with_value else 5
         return self.act_env[:n], self.act_raw[:n], self.logp[:n], self.value[:n]
 
+    def check_status(self):
+        """the tcgen05 rollout forward reports an mbarrier time-out in ws->scal[8] (fm_mlp_tc5.cu); read it once per rollout and
+        fail loudly instead of training on garbage TMEM results"""
+        st = float(self._bufs["scal"][8])
+        if st != 0.0:
+            self._bufs["scal"][8] = 0.0
+            raise RuntimeError(f"tcgen05 MLP forward reported status {st} (mbarrier time-out): results of this rollout are invalid; "
+                               "fm_ppo_use_tcgen05(0) selects the mma.sync path")
+
     def act(self, obs: torch.Tensor, deterministic=False):
         return self.forward(obs, deterministic, with_value=False)[0]
 
@@ -233,17 +258,18 @@ class PPO:
         self.num_timesteps = 0
         self.ep_returns, self.ep_lengths, self.ep_scores = [], [], []
         self.launches = 0
-        self.use_graph, self._graphs, self._idx = use_graph, None, None
+        self.use_graph, self._graphs, self._idx, self._graph_gen = use_graph, None, None, 0
 
     def collect_rollouts(self):
         env, pol = self.env, self.pol
+        c = env.core
         for t in range(self.n_steps):
             act_env, act_raw, logp, val = pol.forward(self.obs)
             self.b_obs[t].copy_(self.obs); self.b_act[t].copy_(act_raw); self.b_logp[t].copy_(logp); self.b_val[t].copy_(val)
-            obs, rew, term, _ = env.step(act_env)
-            self.b_rew[t].copy_(rew); self.b_done[t].copy_(env.core.terminated)
+            obs, rew, term, _ = env.step(act_env, with_infos=False)        # episode statistics stay on the device (env.monitor)
+            self.b_rew[t].copy_(rew); self.b_done[t].copy_(c.terminated)
             self.obs.copy_(obs)
-        self._episode_stats()
+        pol.check_status()
         _, _, _, val = pol.forward(self.obs)
         self.last_val.copy_(val)
         s = torch.cuda.current_stream(self.dev).cuda_stream
@@ -253,9 +279,83 @@ class PPO:
         self.launches += 1
         self.num_timesteps += self.n_steps * env.num_envs * self.world
 
-    def _episode_stats(self):
-        # Monitor / ep_score_history analogue (learning.py:53-72): read once per rollout, not once per step
-        pass
+    def episode_stats(self):
+        """`rollout/ep_rew_mean`, `rollout/ep_len_mean` (SB3 Monitor + logger) and `rollout/ep_score_mean_bucket{k}`
+        (AdditionalMetricsCallback, learning.py:53-72), read from the on-device monitor once per rollout; with several ranks the
+        sums are all-reduced so that every rank logs the job-wide means."""
+        m = self.env.monitor.metrics()
+        if self.world > 1:
+            keys = ["rollout/ep_rew_mean", "rollout/ep_len_mean", "rollout/ep_score_mean_bucket0", "rollout/ep_score_mean_bucket1"]
+            v = torch.tensor([m.get(k, 0.0) for k in keys] + [1.0 if k in m else 0.0 for k in keys], dtype=torch.float64, device=self.dev)
+            torch.distributed.all_reduce(v)
+            for i, k in enumerate(keys):
+                if v[4 + i] > 0:
+                    m[k] = float(v[i] / v[4 + i])
+        return m
+
+    # ---- checkpoints (SyncifiedCheckpointCallback / CheckpointCallback, learning.py:75-86,113-117)
+    def save(self, path, include_env=True):
+        """SB3-layout zip: `policy.pth` (ActorCriticPolicy state-dict), `policy.optimizer.pth` (torch Adam state-dict over the same
+        13 tensors in state-dict order), `data` (hyper-parameters, JSON), `pytorch_variables.pth`, `_stable_baselines3_version`;
+        plus `fm_env_state.npz` (env SoA state, PCG64 streams, monitor) so that a run can RESUME — the reference can only restart."""
+        import json
+        pol = self.pol
+        sd = pol.sb3_state_dict()
+        order = ["log_std"] if not pol.discrete else []
+        order += ["mlp_extractor.policy_net.0.weight", "mlp_extractor.policy_net.0.bias", "mlp_extractor.policy_net.2.weight",
+                  "mlp_extractor.policy_net.2.bias", "mlp_extractor.value_net.0.weight", "mlp_extractor.value_net.0.bias",
+                  "mlp_extractor.value_net.2.weight", "mlp_extractor.value_net.2.bias", "action_net.weight", "action_net.bias",
+                  "value_net.weight", "value_net.bias"]
+        m_sd, v_sd = pol.sb3_state_dict(pol.adam_m), pol.sb3_state_dict(pol.adam_v)
+        opt = {"state": {i: {"step": torch.tensor(float(pol.adam_step)), "exp_avg": m_sd[k], "exp_avg_sq": v_sd[k]} for i, k in enumerate(order)},
+               "param_groups": [{"lr": self.lr, "betas": (0.9, 0.999), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                                 "params": list(range(len(order)))}]}
+        data = {"policy_class": "ActorCriticPolicy", "n_steps": self.n_steps, "batch_size": self.batch_size, "n_epochs": self.n_epochs,
+                "gamma": self.gamma, "gae_lambda": self.lam, "clip_range": self.clip, "vf_coef": self.vf, "ent_coef": self.ent,
+                "learning_rate": self.lr, "max_grad_norm": self.max_norm, "normalize_advantage": self.norm_adv,
+                "num_timesteps": self.num_timesteps, "n_envs": self.env.num_envs, "_n_updates": pol.adam_step,
+                "policy_kwargs": {"net_arch": [128, 128]}, "env_class": self.env.env_class, "num_arms": self.env.num_arms,
+                "adam_step": pol.adam_step, "rollout_seed_calls": pol._call}
+
+        def pth(obj):
+            b = io.BytesIO(); torch.save(obj, b); return b.getvalue()
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("data", json.dumps(data, indent=1))
+            z.writestr("policy.pth", pth(sd)); z.writestr("policy.optimizer.pth", pth(opt)); z.writestr("pytorch_variables.pth", pth({}))
+            z.writestr("_stable_baselines3_version", "2.3.2")
+            if include_env:
+                c, mon = self.env.core, self.env.monitor
+                b = io.BytesIO()
+                np.savez_compressed(b, f=c.f.cpu().numpy(), d=c.d.cpu().numpy(), i=c.i.cpu().numpy(), rng=c.rng.cpu().numpy(),
+                                    obs=self.obs.cpu().numpy(), hist=mon.hist.cpu().numpy(), first=mon.first.cpu().numpy(),
+                                    count=mon.count.cpu().numpy(), ring=mon.ring.cpu().numpy(), ring_head=mon.ring_head.cpu().numpy())
+                z.writestr("fm_env_state.npz", b.getvalue())
+
+    def load(self, path, load_env=True):
+        import json
+        pol = self.pol
+        with zipfile.ZipFile(path) as z:
+            pol.set_sb3_state_dict(torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True))
+            names = z.namelist()
+            if "policy.optimizer.pth" in names:
+                opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu", weights_only=True)
+                order = (["log_std"] if not pol.discrete else []) + [k for k in pol.sb3_state_dict().keys() if k != "log_std"]
+                if opt.get("state"):
+                    pol.set_sb3_state_dict({k: opt["state"][i]["exp_avg"] for i, k in enumerate(order)}, into=pol.adam_m)
+                    pol.set_sb3_state_dict({k: opt["state"][i]["exp_avg_sq"] for i, k in enumerate(order)}, into=pol.adam_v)
+                    pol.adam_step = int(float(opt["state"][0]["step"]))
+            data = json.loads(z.read("data"))
+            self.num_timesteps = int(data.get("num_timesteps", 0))
+            pol._call = int(data.get("rollout_seed_calls", pol._call))
+            if load_env and "fm_env_state.npz" in names:
+                st = np.load(io.BytesIO(z.read("fm_env_state.npz")))
+                c, mon = self.env.core, self.env.monitor
+                for dst, k in ((c.f, "f"), (c.d, "d"), (c.i, "i"), (self.obs, "obs"), (mon.hist, "hist"), (mon.first, "first"),
+                               (mon.count, "count"), (mon.ring, "ring"), (mon.ring_head, "ring_head")):
+                    dst.copy_(torch.from_numpy(st[k]).to(dst.device))
+                c.rng.copy_(torch.from_numpy(st["rng"].view(np.int64)).to(c.rng.device))
+        return self
 
     def _minibatch_eager(self, idx_ptr, step):
         pol = self.pol
@@ -265,8 +365,7 @@ class PPO:
         pol._chk(self.lib.fm_ppo_update(C.byref(pol.net), C.byref(pol._ws), obs.data_ptr(), act.data_ptr(), self.b_logp.data_ptr(),
                                         self.b_adv.data_ptr(), self.b_ret.data_ptr(), idx_ptr, self.batch_size, self.clip, self.vf, self.ent,
                                         int(self.norm_adv), self.stats.data_ptr(), s))
-        if self.world > 1:      # the only inter-GPU exchange of the path: one sum all-reduce of the flat gradient (NCCL / NVLink)
-            torch.distributed.all_reduce(pol.grads, op=torch.distributed.ReduceOp.SUM)
+        _dist.allreduce_sum_(pol.grads)      # the only inter-GPU exchange of the path: one sum all-reduce of the flat gradient (NCCL / NVLink)
         pol._chk(self.lib.fm_adam_step(C.byref(pol.net), self.lr, 0.9, 0.999, self.eps, self.max_norm, 1.0 / self.world, step,
                                        self.stats.data_ptr(), s))
 
@@ -291,6 +390,7 @@ class PPO:
                 pol._chk(self.lib.fm_adam_step(C.byref(pol.net), self.lr, 0.9, 0.999, self.eps, self.max_norm, 1.0 / self.world, 0,
                                                self.stats.data_ptr(), cs()))
         self._graphs = (g_upd, g_adam)
+        self._graph_gen = pol.ws_generation
 
     def train(self):
         pol = self.pol
@@ -299,6 +399,8 @@ class PPO:
         self.stats[:7].zero_()
         n_updates = 0
         # the first call runs launch by launch (it also sets the kernels' attributes); the graphs are captured after it
+        if self._graphs is not None and self._graph_gen != pol.ws_generation:
+            self._graphs = None                      # the workspace was reallocated under the captured graphs: recapture
         use_graph = self.use_graph and self._graphs is not None
         if use_graph:
             self.stats[7:8].fill_(float(pol.adam_step))
@@ -310,7 +412,7 @@ class PPO:
                     self._idx.copy_(perm[b * self.batch_size:(b + 1) * self.batch_size])
                     self._graphs[0].replay()
                     if self.world > 1:
-                        torch.distributed.all_reduce(pol.grads, op=torch.distributed.ReduceOp.SUM)
+                        _dist.allreduce_sum_(pol.grads)
                         self._graphs[1].replay()
                 else:
                     idx = perm[b * self.batch_size:(b + 1) * self.batch_size].contiguous()
@@ -330,5 +432,5 @@ class PPO:
             info = self.train()
             it += 1
             if log:
-                log({"iteration": it, "timesteps": self.num_timesteps, **info})
+                log({"iteration": it, "timesteps": self.num_timesteps, **info, **self.episode_stats()})
         return self

@@ -104,6 +104,11 @@ int fm_ppo_update(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, 
 int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, int step,
                  float* stats, void* stream);
 int fm_ppo_sync_bf16(const fm_ppo_net* net, void* stream);
+/* Monitor / ep_score_history / AdditionalMetricsCallback state (learning.py:53-72,98; environments.py:53,200-201): once per env
+ * step; terminated u8[N] and ep_info f32[N,4] are fm_step's outputs; hist i16[N,100,2], first i16[N,2], count i32[N],
+ * ring f32[100,2] (return, length of the last 100 episodes over all envs), ring_head i32[1] = episodes so far. */
+int fm_monitor_update(const uint8_t* terminated, const float* ep_info, int n, int16_t* hist, int16_t* first, int32_t* count,
+                      float* ring, int32_t* ring_head, void* stream);
 /* fused 3-layer MLP forward of one net on tcgen05 (TMEM accumulators); used by fm_policy_forward unless switched off */
 int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const void* w1, const void* w2, const void* w3,
                        const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
