@@ -33,8 +33,17 @@ struct DevGroupRun {
     asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(32 * W) : "memory");
   }
 };
+// the 32 lanes of a warp working through a sequence of stages (island_newton_warp): a stage is the same code on every lane followed
+// by __syncwarp(); data that crosses stages lives in shared / global memory
+struct DevLanes {
+  int lane;
+  template <class G> __device__ __forceinline__ void stage(G g) { g(lane); __syncwarp(); }
+  __device__ __forceinline__ void sync() { __syncwarp(); }
+};
 struct DevRun {
   template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); __syncthreads(); }
+  // one barrier interval whose work items are taken by whole warps: f(warp index, lanes)
+  template <class F> __device__ __forceinline__ void warps(F f) { DevLanes L{(int)threadIdx.x & 31}; f((int)threadIdx.x >> 5, L); __syncthreads(); }
   // warps [0, WA) run the intervals of progA, warps [WA, WA + WB) those of progB meanwhile; the whole block joins at the end
   template <int WA, int WB, class PA, class PB> __device__ __forceinline__ void split(PA progA, PB progB) {
     if constexpr (WB == 0) {

@@ -59,7 +59,7 @@ static long long fm_dbg_sat[512] = {0};   // general SAT calls by geom1
 // task manager); the pair tests use radii inflated by FM_BROAD_MARGIN, so the cached queue is a superset of the near pairs of every
 // sub-step in between and the narrow phase — which runs every sub-step — produces bit-identical contact sets.
 #ifndef FM_BROAD_MARGIN
-#define FM_BROAD_MARGIN 0.04f
+#define FM_BROAD_MARGIN 0.02f
 #endif
 // Box-box contacts are twice as soft in the reference as MuJoCo's documented regulariser (R = 2 mu^2 (1-d)/d diagApprox, four
 // pyramid rows on each of the four face-clipping points) predicts: every resting cube in runs/*.zip:_last_obs (90 samples, belt
@@ -477,6 +477,24 @@ FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
   }
 }
 
+// phase: explicit inverse of M - hD (implicitfast), one column per thread, from its Cholesky factor in Li.  Stored as a packed
+// symmetric matrix in Lc, whose Cholesky factor of M is dead once ph_arm_minv has run.  ph_integrate then needs two short
+// matrix-vector products per dof instead of a serial 9x9 triangular solve on one lane per arm (that lane set the length of the
+// integration interval: 9.5 % of the sub-step spent waiting for it, profiles/r2d).
+template <int NA, int E>
+FM_HD void ph_arm_winv(EnvS<NA>* S, int tid, int T) {
+  FM_ASSUME_SHARED(S);
+  for (int w = tid; w < NA * 9 * E; w += T) {
+    EnvS<NA>& s = S[w % E]; int ac = w / E; int a = ac / 9, c = ac % 9;
+    float x[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = i == c ? 1.f : 0.f;
+    chol9_solve(s.Li[a], s.chol_d[a][1], x);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) if (i >= c) s.Lc[a][tri(i, c)] = x[i];
+  }
+}
+
 // =====================================================================================================================
 // broad phase: one cluster pair per work item; survivors are queued for the narrow phase.  Every moving cluster has a
 // bounding sphere in shared memory; big geoms (floor, static boxes, belt) have conservative world AABBs in the model.
@@ -494,19 +512,22 @@ template <int NA, int E>
 FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int np = m.n_cluster_pair, s0 = m.cl_sph0;
-  const int stride = T / E;                              // lanes per env; a lane always serves the same env
+  // lanes per env; consecutive lanes serve the same env, so that a warp whose envs all keep their cached queue skips the phase
+  // (with item w -> env w % E every warp would hold lanes of all E envs and run the pair loop for the few stale ones)
+  const int stride = T / E;
   if (tid >= stride * E) return;                         // T need not be a multiple of E: the remainder lanes sit this phase out
-  EnvS<NA>& s = S[tid % E];
+  EnvS<NA>& s = S[tid / stride];
+  const int l0 = tid % stride;
 #ifndef FM_BROAD_ALWAYS
   if (!s.broad_stale) return;                            // the cached queue is still a superset of the near pairs
 #endif
   const float mg = FM_BROAD_MARGIN;
-  for (int cl = tid / E; cl < FmCap<NA>::NCL; cl += stride) {   // remember where this queue was built
+  for (int cl = l0; cl < FmCap<NA>::NCL; cl += stride) {   // remember where this queue was built
     float* rf = s.bnd_ref(cl); const float* bb = s.bnd[cl];
     rf[0] = bb[0]; rf[1] = bb[1]; rf[2] = bb[2]; rf[3] = bb[3];
   }
   const bnd4* bnd = reinterpret_cast<const bnd4*>(&s.bnd[0][0]) - s0;
-  for (int p0 = tid / E; p0 < np; p0 += 4 * stride) {
+  for (int p0 = l0; p0 < np; p0 += 4 * stride) {
     // four pair records are fetched up front so their global-load latencies overlap
     unsigned recs[4];
 #pragma unroll
@@ -804,7 +825,7 @@ FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __rest
       int cs2 = s.c_side[c];
       int n0 = contact_node(cs2, 0), n1 = contact_node(cs2, 1);
       s.c_node[c] = (unsigned char)(n0 >= 0 ? n0 : (n1 >= 0 ? n1 : 255));
-      if (n0 >= 0 && n1 >= 0 && n0 != n1) s.need_union = 1;
+      if (n0 >= 0 && n1 >= 0 && n0 != n1) FM_ATOMIC_OR(&s.need_union, 1);
     }
     st3(s.c_p[c], p); st3(s.c_n[c], n); st3(s.c_t1[c], t1); s.c_mu[c] = mu;
     float K, Bd, imp; impedance_f(pp + 1, pp + 3, dist, m.h, K, Bd, imp);
@@ -911,8 +932,8 @@ FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
     int nraw = s.nraw < FmCap<NA>::CON ? s.nraw : FmCap<NA>::CON;
     s.ncon = nraw;
     s.broad_stale = 0;                                   // consumed by ph_broad of this sub-step
-    FM_DBG(fm_dbg_cnt[0]++; fm_dbg_cnt[1] += nraw; fm_dbg_cnt[2] += s.nqueue; fm_dbg_cnt[3] += s.need_union; for (int k = 0; k < FM_NCUBE; ++k) fm_dbg_cnt[26] += !s.cube_sleep[k];)
-    if (!s.need_union) continue;
+    FM_DBG(fm_dbg_cnt[0]++; fm_dbg_cnt[1] += nraw; fm_dbg_cnt[2] += s.nqueue; fm_dbg_cnt[3] += s.need_union & 1; for (int k = 0; k < FM_NCUBE; ++k) fm_dbg_cnt[26] += !s.cube_sleep[k];)
+    if (!(s.need_union & 1)) continue;
     int* root = s.isl_root;
     for (int c = 0; c < nraw; ++c) {
       int cs = s.c_side[c];
@@ -1239,8 +1260,28 @@ FM_HD bool island_newton_cube(EnvS<NA>& s, const FmDevModel& m, int k, int c0, i
   return ok;
 }
 
-// phase: projected Gauss-Seidel, one lane per constraint island.  Islands whose warm start already satisfies the stopping
-// criterion (every row's update below tol, the steady state of resting contacts) are left as they are.
+// Gauss-Seidel sweeps over one island (exact GS inside the island), starting from the warm start
+template <int NA>
+FM_HD void island_pgs_sweeps(EnvS<NA>& s, const FmDevModel& m, int node, int c0, int c1, bool has_arm, bool single_row, int inner, float tol) {
+  // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
+  // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236);
+  // a lone arm with only its plate equality row is solved exactly by one visit
+  const int cap = (has_arm && c1 > c0) ? 8 * inner : ((c1 == c0 && single_row) ? 1 : inner);
+  for (int it = 0; it < cap; ++it) {
+    float maxd = 0.f;
+    FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0;)
+    for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, 1));
+    for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, contact_visit(s, m, s.isl_list[ci], true));
+    if (maxd < tol) break;
+  }
+}
+
+// phase: constraint solve, one lane per constraint island.  Islands whose warm start already satisfies the stopping
+// criterion (every row's update below tol, the steady state of resting contacts) are left as they are.  One cube against static
+// geoms / the belt: exact active-set Newton on the lane (island_newton_cube).  Islands that couple several nodes or an arm with
+// contacts (grasps, crashes, cube on cube) are only MARKED here (bit 8 + node of need_union) and solved in the next interval by a
+// whole warp each (ph_big_islands).  What is left (a lone arm's limit rows) is swept here.
+#define FM_BIG_BIT(node) (1 << (8 + (node)))
 template <int NA, int E>
 FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
@@ -1256,30 +1297,350 @@ FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
     for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, 2));
     for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, c_res(s, s.isl_list[ci]));
     FM_DBG(fm_dbg_islands++;)
-    FM_DBG(int dbg_kind = has_arm ? (c1 > c0 ? 2 : 1) : 0; int dbg_sw = 0; fm_dbg_cnt[4 + 4 * dbg_kind]++; fm_dbg_cnt[7 + 4 * dbg_kind] += c1 - c0;)
+    FM_DBG(int dbg_kind = has_arm ? (c1 > c0 ? 2 : 1) : 0; fm_dbg_cnt[4 + 4 * dbg_kind]++; fm_dbg_cnt[7 + 4 * dbg_kind] += c1 - c0;)
+    if (maxd < tol) continue;
+    bool alone = true;                                       // no other node was merged into this island
+    if (s.need_union & 1) for (int i = 0; i < NN; ++i) alone = alone && (i == node || s.isl_root[i] != node);
     bool solved = false;
-    if (maxd >= tol && !has_arm && node < FM_NCUBE && c1 - c0 <= 8) {
-      bool alone = true;                                     // no other node was merged into this island
-      if (s.need_union) for (int i = 0; i < NN; ++i) alone = alone && (i == node || s.isl_root[i] != node);
+    if (!has_arm && node < FM_NCUBE && c1 - c0 <= 8 && alone) {
 #ifndef FM_NO_NEWTON
-      if (alone) solved = island_newton_cube(s, m, node, c0, c1, tol);
+      solved = island_newton_cube(s, m, node, c0, c1, tol);
 #endif
-      FM_DBG(if (alone) { fm_dbg_sat[300]++; fm_dbg_sat[301] += solved; })
+      FM_DBG(fm_dbg_sat[300]++; fm_dbg_sat[301] += solved;)
     }
-    if (maxd >= tol && !solved) {
-      // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
-      // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236);
-      // a lone arm with only its plate equality row is solved exactly by one visit
-      const int cap = (has_arm && c1 > c0) ? 8 * inner : ((c1 == c0 && single_row) ? 1 : inner);
-      for (int it = 0; it < cap; ++it) {
-        maxd = 0.f;
-        FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0; dbg_sw++; fm_dbg_cnt[5 + 4 * dbg_kind]++; fm_dbg_cnt[6 + 4 * dbg_kind] += c1 - c0;)
-        for (int a = 0; a < NA; ++a) if (s.isl_root[FM_NCUBE + a] == node) maxd = fmaxf(maxd, arm_rows_visit(s, a, 1));
-        for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, contact_visit(s, m, s.isl_list[ci], true));
-        if (maxd < tol) break;
+    if (solved) continue;
+#ifndef FM_NO_BIG_NEWTON
+    if ((has_arm && c1 > c0) || !alone) { FM_ATOMIC_OR(&s.need_union, FM_BIG_BIT(node)); continue; }   // a warp takes it (ph_big_islands)
+#endif
+    island_pgs_sweeps(s, m, node, c0, c1, has_arm, single_row, inner, tol);
+  }
+}
+
+// =====================================================================================================================
+// Big islands: an arm with contacts (grasp, crash), cube on cube, arm against arm.  Gauss-Seidel on the dual converges slowly on
+// them (a grasp needs all 32 sweeps and still leaves 8 m/s^2) and runs on ONE lane while the block waits.  Here a whole
+// warp solves the island's primal problem exactly, like island_newton_cube does for a lone cube:
+//   min_a 1/2 (a - a0)^T M (a - a0) + sum_rows s_r(J_r a - aref_r),  s_r(x) = x^2 / (2 R_r) for x < 0 (always, for equality rows)
+// over the island's <= 24 accelerations (9 per arm, 6 per cube; the belt dof is held at its lagged acceleration).  Active-set
+// Newton: the rows with x < 0 at the current a form the set; (M + sum J^T J / R) a = M a0 + sum J^T aref / R by a Jacobi-scaled
+// Cholesky factorisation; repeat until the set is stable.  The warp works in stages separated by __syncwarp(); everything that
+// crosses a stage lives in shared memory that is dead at this point of the sub-step (the Newton-Euler scratch d_f, d_n, d_comp and
+// the raw-contact keys), so the same source runs in the host-compiled test build with a loop over the 32 lanes per stage.
+#define FM_BIG_NU 24
+#define FM_BIG_NC 24
+// generalised force of arm dof d without constraints: actuator - bias (same expressions as ph_smooth)
+template <int NA>
+FM_HD float arm_qfrc(const EnvS<NA>& s, const FmDevModel& m, int a, int d) {
+  if (d < 7) {
+    float c = clampf(s.ctrl_target[1 + 8 * a + d], m.ctrl_lo[1 + d], m.ctrl_hi[1 + d]);
+    return m.kp * (c - s.arm_q[a][d]) - m.kd * s.arm_v[a][d] - s.bias[a][d];
+  }
+  float c = clampf(s.ctrl_target[1 + 8 * a + 7], m.ctrl_lo[8], m.ctrl_hi[8]);
+  float len = m.ten0 * s.arm_q[a][7] + m.ten1 * s.arm_q[a][8], lv = m.ten0 * s.arm_v[a][7] + m.ten1 * s.arm_v[a][8];
+  float f = clampf(m.g_kp * c - m.g_kb * len - m.g_kd * lv, m.g_fmin, m.g_fmax);
+  return (d == 7 ? m.ten0 : m.ten1) * f - s.bias[a][d];
+}
+
+template <int NA>
+struct BigIsl {
+  EnvS<NA>& s; const FmDevModel& m;
+  int nnode, nodes[4], off[5], NU, c0, nc, nrow_arm, arm_row0[4];
+  float *H, *g, *a, *Jc, *Wg; unsigned *act, *prev; int* chg;
+  FM_HDM BigIsl(EnvS<NA>& s_, const FmDevModel& m_) : s(s_), m(m_) {}
+  // unknown j -> (index into nodes, local dof)
+  FM_HDM void unk(int j, int& ni, int& q) const { ni = 0; while (ni + 1 < nnode && off[ni + 1] <= j) ++ni; q = j - off[ni]; }
+  FM_HDM int acc_index(int ni, int q) const { int nd = nodes[ni]; return nd < FM_NCUBE ? 1 + 6 * nd + q : 61 + 9 * (nd - FM_NCUBE) + q; }
+  FM_HDM int node_slot(int node) const { for (int i = 0; i < nnode; ++i) if (nodes[i] == node) return i; return -1; }
+  // column j of the contact's base Jacobian (rows n, t1, t2): sum over the contact's two sides
+  FM_HDM void jcol(int c, int j, float* out) const {
+    out[0] = out[1] = out[2] = 0.f;
+    int ni, q; unk(j, ni, q);
+    const int node = nodes[ni];
+    const int cs = s.c_side[c];
+    const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+    for (int sd_i = 0; sd_i < 2; ++sd_i) {
+      const int sd = (cs >> (FM_SIDE_BITS * sd_i)) & FM_SIDE_MASK;
+      const int ty = side_type(sd), ix = side_idx(sd);
+      const float sg = sd_i ? 1.f : -1.f;
+      if (ty == FM_SIDE_CUBE && ix == node) {
+        const f3 r = ld3(s.c_p[c]) - ld3(s.cube_x[ix]);
+        const f3 d[3] = {n, t1, t2};
+        for (int k = 0; k < 3; ++k) { f3 v = q < 3 ? d[k] : cross3(r, d[k]); out[k] += sg * comp3(v, q % 3); }
+      } else if (ty == FM_SIDE_ARM && FM_NCUBE + (ix >> 4) == node) {
+        const float* J = s.as_J[side_slot(sd)];
+        for (int k = 0; k < 3; ++k) out[k] += sg * J[9 * k + q];
       }
     }
-    FM_DBG(fm_dbg_cnt[16 + (dbg_sw < 9 ? dbg_sw : 9)] += (dbg_kind == 0);)
+  }
+  // contact-space acceleration u = J_c a + (belt part) of contact c at the island accelerations `av`
+  FM_HDM void contact_u(int c, const float* av, float* u) const {
+    belt_const(c, u);
+    const int cs = s.c_side[c];
+    const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+    for (int sd_i = 0; sd_i < 2; ++sd_i) {
+      const int sd = (cs >> (FM_SIDE_BITS * sd_i)) & FM_SIDE_MASK;
+      const int ty = side_type(sd), ix = side_idx(sd);
+      const float sg = sd_i ? 1.f : -1.f;
+      if (ty == FM_SIDE_CUBE) {
+        const int ni = node_slot(ix); if (ni < 0) continue;
+        const float* v = av + off[ni];
+        const f3 pv = mk3(v[0], v[1], v[2]) + cross3(mk3(v[3], v[4], v[5]), ld3(s.c_p[c]) - ld3(s.cube_x[ix]));
+        u[0] += sg * dot3(n, pv); u[1] += sg * dot3(t1, pv); u[2] += sg * dot3(t2, pv);
+      } else if (ty == FM_SIDE_ARM) {
+        const int ni = node_slot(FM_NCUBE + (ix >> 4)); if (ni < 0) continue;
+        const float* v = av + off[ni]; const float* J = s.as_J[side_slot(sd)];
+        for (int d = 0; d < 3; ++d) { float acc = 0.f; for (int k = 0; k < 9; ++k) acc += J[9 * d + k] * v[k]; u[d] += sg * acc; }
+      }
+    }
+  }
+  // constant part of the contact-space acceleration: the belt side (dof held at its lagged acceleration)
+  FM_HDM void belt_const(int c, float* kb) const {
+    kb[0] = kb[1] = kb[2] = 0.f;
+    const int cs = s.c_side[c];
+    for (int sd_i = 0; sd_i < 2; ++sd_i) {
+      const int sd = (cs >> (FM_SIDE_BITS * sd_i)) & FM_SIDE_MASK;
+      if (side_type(sd) != FM_SIDE_BELT) continue;
+      const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+      const float sg = sd_i ? 1.f : -1.f, ab = s.acc[0];
+      kb[0] += sg * n.y * ab; kb[1] += sg * t1.y * ab; kb[2] += sg * t2.y * ab;
+    }
+  }
+};
+
+template <int NA, class Lanes>
+FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes& L, float tol) {
+  const int NN = EnvS<NA>::NNODE;
+  BigIsl<NA> B(s, m);
+  B.nnode = 0; B.NU = 0; B.nrow_arm = 0;
+  for (int i = 0; i < NN; ++i)
+    if (s.isl_root[i] == root) {
+      if (B.nnode == 4) return false;
+      B.nodes[B.nnode] = i; B.off[B.nnode] = B.NU; B.NU += i >= FM_NCUBE ? 9 : 6;
+      if (i >= FM_NCUBE) { B.arm_row0[B.nnode] = B.nrow_arm; B.nrow_arm += s.arow_n[i - FM_NCUBE]; } else B.arm_row0[B.nnode] = 0;
+      B.nnode++;
+    }
+  B.off[B.nnode] = B.NU;
+  B.c0 = s.isl_start[root]; B.nc = s.isl_start[root + 1] - B.c0;
+  const int NU = B.NU, nc = B.nc, nrows = 4 * nc + B.nrow_arm;
+  if (NU > FM_BIG_NU || nc > FM_BIG_NC || nc + B.nrow_arm > 32 || nrows > 128) return false;
+  // scratch: H (packed lower triangle, 300), g (24), a (24) in the dead Newton-Euler buffers; staging + bit sets in the raw keys
+  B.H = &s.d_f[0][0][0]; B.g = B.H + 300; B.a = B.g + 24;
+  float* rb = reinterpret_cast<float*>(&s.raw_key[0]);
+  B.Jc = rb; B.Wg = rb + 72; B.act = reinterpret_cast<unsigned*>(rb + 81); B.prev = B.act + 4; B.chg = reinterpret_cast<int*>(B.prev + 4);
+  const int NH = NU * (NU + 1) / 2;
+  L.stage([&](int lane) {
+    if (lane < NU) { int ni, q; B.unk(lane, ni, q); B.a[lane] = s.acc[B.acc_index(ni, q)]; }
+    if (lane < 4) { B.act[lane] = 0u; B.prev[lane] = 0xFFFFFFFFu; }
+  });
+  bool ok = false;
+  for (int it = 0; it < 7; ++it) {
+    FM_DBG(fm_dbg_sat[331]++;)
+    // ---- active set at the current a: one lane per contact (4 rows) or per arm row
+    L.stage([&](int lane) { if (lane < 4) B.act[lane] = 0u; if (lane == 0) *B.chg = 0; });
+    L.stage([&](int lane) {
+      if (lane < nc) {
+        const int c = s.isl_list[B.c0 + lane];
+        float u[3]; B.contact_u(c, B.a, u);
+        const float mu = s.c_mu[c];
+        unsigned bits = 0; float mx = 0.f;
+        for (int r = 0; r < 4; ++r) {
+          const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+          const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
+          const bool on = x < 0.f;
+          const int bit = 4 * lane + r;
+          if (on) bits |= 1u << (bit & 31);
+          if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) mx = fmaxf(mx, fabsf(x));
+        }
+        FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[(4 * lane) >> 5]), (int)bits);
+        int mi; memcpy(&mi, &mx, 4); FM_ATOMIC_MAXI(B.chg, mi);
+      } else if (lane < nc + B.nrow_arm) {
+        int rr = lane - nc, ni = 0;
+        while (!(B.nodes[ni] >= FM_NCUBE && rr >= B.arm_row0[ni] && rr < B.arm_row0[ni] + s.arow_n[B.nodes[ni] - FM_NCUBE])) ++ni;
+        const int a = B.nodes[ni] - FM_NCUBE, r = rr - B.arm_row0[ni];
+        const int code = s.arow_code[a][r];
+        const float* aa = B.a + B.off[ni];
+        float x; bool on;
+        if (code & 0x1000) { x = aa[7] - aa[8] - s.arow_aref[a][r]; on = true; }
+        else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; x = sg * aa[d] - s.arow_aref[a][r]; on = x < 0.f; }
+        const int bit = 4 * nc + rr;
+        if (on) FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[bit >> 5]), (int)(1u << (bit & 31)));
+        if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) { float ax = fabsf(x); int mi; memcpy(&mi, &ax, 4); FM_ATOMIC_MAXI(B.chg, mi); }
+      }
+    });
+    {
+      bool same = true;
+      for (int w = 0; w < 4; ++w) same = same && B.act[w] == B.prev[w];
+      float cg; memcpy(&cg, B.chg, 4);
+      L.sync();                                               // every lane has read act / prev before the next stage rewrites them
+      if (it > 0 && (same || cg < tol)) { ok = true; break; }
+      if (it == 6) break;
+    }
+    // ---- assemble H = M + sum_active J^T J / R and g = M a0 + sum_active J^T aref / R
+    L.stage([&](int lane) {
+      for (int idx = lane; idx < NH; idx += 32) B.H[idx] = 0.f;
+      if (lane < NU) {
+        int ni, q; B.unk(lane, ni, q);
+        const int nd = B.nodes[ni];
+        B.g[lane] = nd < FM_NCUBE ? (q == 2 ? -m.g / m.cube_invm[nd] : 0.f) : arm_qfrc(s, m, nd - FM_NCUBE, q);
+      }
+      if (lane < 4) B.prev[lane] = B.act[lane];
+    });
+    L.stage([&](int lane) {      // the nodes' inertia blocks
+      for (int idx = lane; idx < NH; idx += 32) {
+        int i = 0; while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+        const int j = idx - i * (i + 1) / 2;
+        int ni, qi, nj, qj; B.unk(i, ni, qi); B.unk(j, nj, qj);
+        if (ni != nj) continue;
+        const int nd = B.nodes[ni];
+        if (nd < FM_NCUBE) { if (qi == qj) B.H[idx] = qi < 3 ? 1.f / m.cube_invm[nd] : 1.f / m.cube_invI[nd]; }
+        else B.H[idx] = s.M[nd - FM_NCUBE][tri(qi, qj)];
+      }
+    });
+    for (int ci = 0; ci < nc; ++ci) {
+      const int c = s.isl_list[B.c0 + ci];
+      L.stage([&](int lane) {
+        if (lane < NU) { float jc[3]; B.jcol(c, lane, jc); B.Jc[lane] = jc[0]; B.Jc[24 + lane] = jc[1]; B.Jc[48 + lane] = jc[2]; }
+        if (lane == 31) {      // 3x3 weight of the contact's active pyramid rows and the matching right-hand side
+          float W[6] = {0, 0, 0, 0, 0, 0}, gc[3] = {0, 0, 0}, kb[3];
+          B.belt_const(c, kb);
+          const float mu = s.c_mu[c], D = 1.f / s.c_R[c];
+          for (int r = 0; r < 4; ++r) {
+            const int bit = 4 * ci + r;
+            if (!((B.act[bit >> 5] >> (bit & 31)) & 1u)) continue;
+            const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+            const float rhs = D * (s.c_aref[c][r] - kb[0] - cf * kb[tq]);
+            W[0] += D; W[tq] += D * cf * cf; W[2 + tq] += D * cf;      // (0,0) (tq,tq) (0,tq); W = [00, 11, 22, 01, 02, 12]
+            gc[0] += rhs; gc[tq] += cf * rhs;
+          }
+          for (int k = 0; k < 6; ++k) B.Wg[k] = W[k];
+          for (int k = 0; k < 3; ++k) B.Wg[6 + k] = gc[k];
+        }
+      });
+      L.stage([&](int lane) {
+        const float W00 = B.Wg[0], W11 = B.Wg[1], W22 = B.Wg[2], W01 = B.Wg[3], W02 = B.Wg[4];
+        if (lane < NU) B.g[lane] += B.Jc[lane] * B.Wg[6] + B.Jc[24 + lane] * B.Wg[7] + B.Jc[48 + lane] * B.Wg[8];
+        for (int idx = lane; idx < NH; idx += 32) {
+          int i = 0; while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+          const int j = idx - i * (i + 1) / 2;
+          const float i0 = B.Jc[i], i1 = B.Jc[24 + i], i2 = B.Jc[48 + i];
+          if (i0 == 0.f && i1 == 0.f && i2 == 0.f) continue;
+          const float j0 = B.Jc[j], j1 = B.Jc[24 + j], j2 = B.Jc[48 + j];
+          const float t0 = W00 * j0 + W01 * j1 + W02 * j2, t1 = W01 * j0 + W11 * j1, t2 = W02 * j0 + W22 * j2;   // the pyramid has no (t1, t2) term
+          B.H[idx] += i0 * t0 + i1 * t1 + i2 * t2;
+        }
+      });
+    }
+    L.stage([&](int lane) {      // arm-local rows (one or two non-zeros each): lane 0, in row order
+      if (lane != 0) return;
+      for (int ni = 0; ni < B.nnode; ++ni) {
+        if (B.nodes[ni] < FM_NCUBE) continue;
+        const int a = B.nodes[ni] - FM_NCUBE, o = B.off[ni];
+        for (int r = 0; r < s.arow_n[a]; ++r) {
+          const int bit = 4 * nc + B.arm_row0[ni] + r;
+          if (!((B.act[bit >> 5] >> (bit & 31)) & 1u)) continue;
+          const int code = s.arow_code[a][r]; const float D = 1.f / s.arow_R[a][r], ar = s.arow_aref[a][r];
+          if (code & 0x1000) {
+            const int i7 = o + 7, i8 = o + 8;
+            B.H[tri(i7, i7)] += D; B.H[tri(i8, i8)] += D; B.H[tri(i8, i7)] -= D;
+            B.g[i7] += D * ar; B.g[i8] -= D * ar;
+          } else {
+            const int d = o + (code & 255); const float sg = (code >> 8) ? -1.f : 1.f;
+            B.H[tri(d, d)] += D; B.g[d] += sg * D * ar;
+          }
+        }
+      }
+    });
+    // ---- Jacobi scaling (the arm's inertias span three decades), Cholesky, two triangular solves: all in place
+    L.stage([&](int lane) { if (lane < NU) B.a[lane] = rsqrtf(fmaxf(B.H[tri(lane, lane)], 1e-30f)); });
+    L.stage([&](int lane) {
+      for (int idx = lane; idx < NH; idx += 32) { int i = 0; while ((i + 1) * (i + 2) / 2 <= idx) ++i; const int j = idx - i * (i + 1) / 2; B.H[idx] *= B.a[i] * B.a[j]; }
+      if (lane < NU) B.g[lane] *= B.a[lane];
+    });
+    for (int k = 0; k < NU; ++k) {
+      L.stage([&](int lane) {      // column k: L[i][k] = H[i][k] / sqrt(H[k][k]) for i >= k
+        const float piv = rsqrtf(fmaxf(B.H[tri(k, k)], 1e-30f));
+        const int i = k + lane;
+        if (i < NU && i > k) B.H[tri(i, k)] *= piv;
+      });
+      L.stage([&](int lane) {      // the pivot itself, then the trailing update
+        if (lane == 0) B.H[tri(k, k)] = sqrtf(fmaxf(B.H[tri(k, k)], 1e-30f));
+        const int n1 = NU - k - 1;
+        for (int e = lane; e < n1 * (n1 + 1) / 2; e += 32) {
+          int ii = 0; while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+          const int jj = e - ii * (ii + 1) / 2;
+          const int i = k + 1 + ii, j = k + 1 + jj;
+          B.H[tri(i, j)] -= B.H[tri(i, k)] * B.H[tri(j, k)];
+        }
+      });
+    }
+    L.stage([&](int lane) {        // forward and backward substitution on lane 0 (24 x 24: ~600 multiply-adds), then un-scale
+      if (lane != 0) return;
+      float y[FM_BIG_NU];
+      for (int i = 0; i < NU; ++i) { float v = B.g[i]; for (int q = 0; q < i; ++q) v -= B.H[tri(i, q)] * y[q]; y[i] = v / B.H[tri(i, i)]; }
+      for (int i = NU - 1; i >= 0; --i) { float v = y[i]; for (int q = i + 1; q < NU; ++q) v -= B.H[tri(q, i)] * y[q]; y[i] = v / B.H[tri(i, i)]; }
+      for (int i = 0; i < NU; ++i) B.g[i] = y[i];
+    });
+    L.stage([&](int lane) { if (lane < NU) B.a[lane] *= B.g[lane]; });
+  }
+  FM_DBG(fm_dbg_sat[332] += ok;)
+  if (!ok) return false;
+  // ---- accept: accelerations, forces f = max(-x, 0) / R of the final a, belt projections
+  L.stage([&](int lane) {
+    if (lane < NU) { int ni, q; B.unk(lane, ni, q); s.acc[B.acc_index(ni, q)] = B.a[lane]; }
+    if (lane < nc) {
+      const int c = s.isl_list[B.c0 + lane];
+      float u[3]; B.contact_u(c, B.a, u);
+      const float mu = s.c_mu[c], D = 1.f / s.c_R[c];
+      float f[4];
+      for (int r = 0; r < 4; ++r) {
+        const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+        const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
+        f[r] = x < 0.f ? -D * x : 0.f;
+        s.c_f[c][r] = f[r];
+      }
+      float bs = 0.f;
+      const int cs = s.c_side[c];
+      for (int sd_i = 0; sd_i < 2; ++sd_i) {
+        const int sd = (cs >> (FM_SIDE_BITS * sd_i)) & FM_SIDE_MASK;
+        if (side_type(sd) != FM_SIDE_BELT) continue;
+        const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+        const float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
+        bs += (sd_i ? 1.f : -1.f) * (n.y * Fn + t1.y * F1 + t2.y * F2);
+      }
+      c_belt(s, c) = bs;
+    } else if (lane < nc + B.nrow_arm) {
+      int rr = lane - nc, ni = 0;
+      while (!(B.nodes[ni] >= FM_NCUBE && rr >= B.arm_row0[ni] && rr < B.arm_row0[ni] + s.arow_n[B.nodes[ni] - FM_NCUBE])) ++ni;
+      const int a = B.nodes[ni] - FM_NCUBE, r = rr - B.arm_row0[ni];
+      const int code = s.arow_code[a][r];
+      const float* aa = B.a + B.off[ni];
+      const float D = 1.f / s.arow_R[a][r];
+      if (code & 0x1000) s.arow_f[a][r] = -D * (aa[7] - aa[8] - s.arow_aref[a][r]);
+      else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; const float x = sg * aa[d] - s.arow_aref[a][r]; s.arow_f[a][r] = x < 0.f ? -D * x : 0.f; }
+    }
+  });
+  return true;
+}
+
+// phase: one warp per marked island (see ph_pgs); an island the Newton cannot take or settle falls back to the sweeps on one lane
+template <int NA, int E, class Lanes>
+FM_HD void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps, Lanes& L, int inner, float tol) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
+  const int NN = EnvS<NA>::NNODE;
+  for (int w = warp; w < NN * E; w += nwarps) {
+    EnvS<NA>& s = S[w % E]; const int node = w / E;
+    if (!(s.need_union & FM_BIG_BIT(node))) continue;
+    FM_DBG(fm_dbg_sat[330]++;)
+    const bool ok = island_newton_warp<NA>(s, m, node, L, tol);
+    if (!ok) {
+      L.stage([&](int lane) {
+        if (lane != 0) return;
+        const int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
+        bool has_arm = false;
+        for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
+        island_pgs_sweeps(s, m, node, c0, c1, has_arm, false, inner, tol);
+      });
+    }
   }
 }
 
@@ -1316,7 +1677,7 @@ FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
 template <int NA, int E>
 FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-  const int per = 1 + FM_NCUBE + NA;
+  const int per = 1 + FM_NCUBE + 9 * NA;
   for (int w = tid; w < per * E; w += T) {
     EnvS<NA>& s = S[w % E]; int i = w / E;
     float h = m.h;
@@ -1352,24 +1713,25 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       }
       q[3] = qq.w; q[4] = qq.x; q[5] = qq.y; q[6] = qq.z;
     } else {
-      int a = i - 1 - FM_NCUBE;
-      float* acc = &s.acc[61 + 9 * a];
-      float y[9];
-      for (int r = 0; r < 9; ++r) {
-        float sum = 0.f;
-        for (int k = 0; k < 9; ++k) sum += s.M[a][r >= k ? tri(r, k) : tri(k, r)] * acc[k];
-        y[r] = sum;
+      // arm dof r: qacc_r = [(M - hD)^-1 M acc]_r; every lane forms y = M acc itself (81 multiply-adds, nine independent sums)
+      const int ad = i - 1 - FM_NCUBE; const int a = ad / 9, r = ad % 9;
+      const float* acc = &s.acc[61 + 9 * a]; const float* Mp = s.M[a]; const float* Wp = s.Lc[a];
+      float qa = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float yk = 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) yk += Mp[k >= j ? tri(k, j) : tri(j, k)] * acc[j];
+        qa += Wp[r >= k ? tri(r, k) : tri(k, r)] * yk;
       }
-      chol9_solve(s.Li[a], s.chol_d[a][1], y);
+      const float vn = s.arm_v[a][r] + h * qa;
+      s.arm_v[a][r] = vn;
+      // compensated like the cube positions: a joint creeping to its target at < 6e-5 rad/s would otherwise stall 1e-5 rad short
       float* ql = s.arm_qlo(a);
-      for (int r = 0; r < 9; ++r) {
-        s.arm_v[a][r] += h * y[r];
-        // compensated like the cube positions: a joint creeping to its target at < 6e-5 rad/s would otherwise stall 1e-5 rad short
-        float q0 = s.arm_q[a][r], inc = h * s.arm_v[a][r] + ql[r];
-        float nq = q0 + inc;
-        ql[r] = inc - (nq - q0);
-        s.arm_q[a][r] = nq;
-      }
+      const float q0 = s.arm_q[a][r], inc = h * vn + ql[r];
+      const float nq = q0 + inc;
+      ql[r] = inc - (nq - q0);
+      s.arm_q[a][r] = nq;
     }
   }
 }

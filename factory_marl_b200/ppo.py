@@ -316,7 +316,8 @@ class PPO:
                 "learning_rate": self.lr, "max_grad_norm": self.max_norm, "normalize_advantage": self.norm_adv,
                 "num_timesteps": self.num_timesteps, "n_envs": self.env.num_envs, "_n_updates": pol.adam_step,
                 "policy_kwargs": {"net_arch": [128, 128]}, "env_class": self.env.env_class, "num_arms": self.env.num_arms,
-                "adam_step": pol.adam_step, "rollout_seed_calls": pol._call}
+                "adam_step": pol.adam_step, "rollout_seed_calls": pol._call, "policy_seed": pol.seed,
+                "perm_generator_state": self.gen.get_state().cpu().numpy().tolist()}
 
         def pth(obj):
             b = io.BytesIO(); torch.save(obj, b); return b.getvalue()
@@ -347,7 +348,9 @@ class PPO:
                     pol.adam_step = int(float(opt["state"][0]["step"]))
             data = json.loads(z.read("data"))
             self.num_timesteps = int(data.get("num_timesteps", 0))
-            pol._call = int(data.get("rollout_seed_calls", pol._call))
+            pol._call = int(data.get("rollout_seed_calls", pol._call)); pol.seed = int(data.get("policy_seed", pol.seed))
+            if "perm_generator_state" in data:
+                self.gen.set_state(torch.tensor(data["perm_generator_state"], dtype=torch.uint8))
             if load_env and "fm_env_state.npz" in names:
                 st = np.load(io.BytesIO(z.read("fm_env_state.npz")))
                 c, mon = self.env.core, self.env.monitor

@@ -15,8 +15,18 @@ static thread_local std::string g_err;
 // thread ids of one barrier interval are executed in ascending, descending or a fixed shuffled order (fm_emu_set_order):
 // a result that depends on that order reveals an intra-interval read-after-write, i.e. a missing barrier on the GPU.
 static int g_order = 0;
+// a warp's stages (island_newton_warp): each stage is executed for the 32 lanes one after the other, in the order under test
+struct HostLanes {
+  template <class G> void stage(G g) {
+    if (g_order == 0) for (int l = 0; l < 32; ++l) g(l);
+    else if (g_order == 1) for (int l = 31; l >= 0; --l) g(l);
+    else for (int k = 0; k < 32; ++k) g((k * 13 + 5) % 32);
+  }
+  void sync() {}
+};
 struct HostRun {
   int T;
+  template <class F> void warps(F f) { HostLanes L; for (int w = 0; w < T / 32; ++w) f(g_order == 1 ? T / 32 - 1 - w : w, L); }
   template <class F> void operator()(F f) {
     if (g_order == 0) for (int t = 0; t < T; ++t) f(t);
     else if (g_order == 1) for (int t = T - 1; t >= 0; --t) f(t);

@@ -45,14 +45,15 @@ def test_lazy_infos_and_monitor_match_a_python_monitor():
     assert env.get_attr("ep_score_history") == hist
     m = env.monitor.metrics()
     assert m["episodes"] == len(eps)
-    # all 64 envs finished >= 1 episode -> bucket means exist (all scores are 0 here); ring = last 100 episodes
-    assert m["rollout/ep_score_mean_bucket0"] == 0.0 and m["rollout/ep_score_mean_bucket1"] == 0.0
-    last = sorted(eps[-100:]) if False else None
+    if all(hist):       # learning.py:64: the bucket means exist once no env has an empty history (all scores are 0 here)
+        assert m["rollout/ep_score_mean_bucket0"] == 0.0 and m["rollout/ep_score_mean_bucket1"] == 0.0
+    else:
+        assert "rollout/ep_score_mean_bucket0" not in m
     assert abs(m["rollout/ep_len_mean"] - np.mean([l for _, l in eps])) < 5      # same population up to which 100 the ring kept
-    stale = infos
+    _, _, _, unread = env.step(a)
     env.step(a)
-    with pytest.raises(RuntimeError):
-        stale[0]
+    with pytest.raises(RuntimeError):      # lazy infos are built from the step's device outputs: they must be read before the next step
+        unread[0]
 
 
 def test_monitor_bucket_means_reproduce_the_reference_indexing():
@@ -107,10 +108,14 @@ def test_checkpoint_roundtrip_resumes_bit_exactly(tmp_path):
     b.load(p)
     assert torch.equal(a.pol.params, b.pol.params) and torch.equal(a.pol.adam_m, b.pol.adam_m) and torch.equal(a.pol.adam_v, b.pol.adam_v)
     assert torch.equal(a.env.core.f, b.env.core.f) and torch.equal(a.env.core.i, b.env.core.i) and torch.equal(a.env.core.rng, b.env.core.rng)
-    b.gen.set_state(a.gen.get_state())
     for ppo in (a, b):
-        ppo.collect_rollouts(); ppo.train()
-    assert torch.equal(a.pol.params, b.pol.params) and torch.equal(a.obs, b.obs)
+        ppo.collect_rollouts()
+    # the resumed rollout is bit-identical: same env state, same PCG64 / action-noise streams, same parameters
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.b_obs, b.b_obs) and torch.equal(a.b_act, b.b_act) and torch.equal(a.b_adv, b.b_adv)
+    for ppo in (a, b):
+        ppo.train()
+    # the update accumulates weight gradients with split-K float atomics: equal up to summation order
+    assert float((a.pol.params - b.pol.params).abs().max()) < 1e-5
 
 
 @pytest.mark.parametrize("run", ["r666unuv", "rk5rxnav", "xfwgqibb", "y6lp1j7k"])
