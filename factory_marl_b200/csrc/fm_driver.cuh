@@ -82,7 +82,13 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
         sub([&](int tid) { ph_arm_chol_col<NA, E, 7>(S, tid, TA); });
         sub([&](int tid) { ph_arm_chol_col<NA, E, 8>(S, tid, TA); });
         sub([&](int tid) { ph_arm_minv<NA, E>(S, tid, TA); ph_arm_rows<NA, E>(S, m, tid, TA); });   // the arm-local rows need no contact
-        sub([&](int tid) { ph_arm_winv<NA, E>(S, tid, TA); });                                       // Lc is dead now: (M - hD)^-1 goes there
+#ifndef FM_INTEGRATE_SERIAL
+        sub([&](int tid) { ph_arm_winv<NA, E>(S, tid, TA);
+#if !defined(FM_NARROW_STATIC)
+                           if (WB > 0) ph_narrow_steal<NA, E>(S, m, cpairs, tid & 31);   // group A is done: help group B with the narrow phase
+#endif
+        });                                       // Lc is dead now: (M - hD)^-1 goes there
+#endif
       },
       [&](auto& sub, int TB) {
         sub([&](int tid) { ph_narrow<NA, E>(S, m, cpairs, tid, TB); });
@@ -117,7 +123,7 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
 }
 
 // TW = warps per block (default: one warp per env of the block)
-template <int NA, int E, int TW = E, class Run>
+template <int NA, int E, int TW = E, bool BIGN = false, class Run>
 FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class,
                          const FmEnvCfg& cfg, const FmStatePtrs& st, const FmStepArgs& ar, int env0) {
   const int T = 32 * TW;
@@ -155,8 +161,10 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, 
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 1); });
     run([&](int tid) { ph_check<NA, E>(S, m, tid, T); });
-    run([&](int tid) { ph_pgs<NA, E>(S, m, tid, T, cfg.pgs_inner, cfg.pgs_tol); });
-    run.warps([&](int warp, auto& L) { ph_big_islands<NA, E>(S, m, warp, TW, L, cfg.pgs_inner, cfg.pgs_tol); });
+    run([&](int tid) { ph_pgs<NA, E, BIGN>(S, m, tid, T, cfg.pgs_inner, cfg.pgs_tol); });
+    // BIGN: the kernel variant of the IK-driven env classes, where arms grasp and an arm + contact island is the common hard case.
+    // Compiled separately: the mere presence of this phase in the fused loop costs the other classes 19 % (profiles/README r2i)
+    if constexpr (BIGN) run.warps([&](int warp, auto& L) { ph_big_islands<NA, E>(S, m, warp, TW, L, cfg.pgs_inner, cfg.pgs_tol); });
     // belt lane: contact term of the belt dof (same lane as the belt row of ph_integrate), then integration
     run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 2); });

@@ -20,7 +20,7 @@
 #endif
 struct FmLaunch { const FmDevModel* model; const unsigned int* cpairs; const int* geom_class; FmEnvCfg cfg; FmStatePtrs st; };
 
-template <int NA, int E, int TW>
+template <int NA, int E, int TW, bool BIGN = false>
 cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t s);
 
 #ifdef FM_KERNEL_IMPL
@@ -56,7 +56,7 @@ struct DevRun {
   }
 };
 
-template <int NA, int E, int TW>
+template <int NA, int E, int TW, bool BIGN>
 __global__ void __launch_bounds__(32 * TW, FM_MINBLK) fm_step_kernel(const FmDevModel* __restrict__ mp, const unsigned int* __restrict__ cpairs,
                                                              const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,27 +71,27 @@ __global__ void __launch_bounds__(32 * TW, FM_MINBLK) fm_step_kernel(const FmDev
   }
   __builtin_assume(__isShared(S)); __builtin_assume(__isShared(TS));
   DevRun run;
-  fm_block_step<NA, E, TW>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
+  fm_block_step<NA, E, TW, BIGN>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
 }
 
-template <int NA, int E, int TW>
+template <int NA, int E, int TW, bool BIGN>
 cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t s) {
   const size_t smem = E * (sizeof(EnvS<NA>) + sizeof(TaskS));
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fm_step_kernel<NA, E, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {   // per device, not per process: set on every launch (cheap) so that a second GPU in the same process gets it too
+    cudaError_t e = cudaFuncSetAttribute(fm_step_kernel<NA, E, TW, BIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int nblk = (L.st.n + E - 1) / E;
-  fm_step_kernel<NA, E, TW><<<nblk, 32 * TW, smem, s>>>(L.model, L.cpairs, L.geom_class, L.cfg, L.st, ar);
+  fm_step_kernel<NA, E, TW, BIGN><<<nblk, 32 * TW, smem, s>>>(L.model, L.cpairs, L.geom_class, L.cfg, L.st, ar);
   return cudaGetLastError();
 }
 #else
 extern template cudaError_t fm_launch_step<2, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<2, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW, true>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW, true>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 #endif

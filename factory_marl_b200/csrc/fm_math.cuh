@@ -15,6 +15,14 @@
 #define FM_D static inline
 #endif
 
+// barrier-interval phase functions (ph_*): with FM_PHASE_NOINLINE each is its own function, so that ptxas allocates registers
+// per phase instead of across the whole fused sub-step loop (state crosses phases through shared memory anyway)
+#if defined(FM_PHASE_NOINLINE) && defined(__CUDACC__)
+#define FM_PH FM_HDN
+#else
+#define FM_PH FM_HD
+#endif
+
 #if !defined(__CUDACC__)
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline void sincosf_host(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }

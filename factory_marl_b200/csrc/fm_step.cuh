@@ -187,7 +187,7 @@ FM_HD void broad_check(EnvS<NA>& s, int cl, const float* bb) {
 // =====================================================================================================================
 // phase: cube kinematics (normalise quats in place as mj_kinematics does [3P])
 template <int NA, int E>
-FM_HD void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int sleep_hidden) {
+FM_PH void ph_cube_derive(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int sleep_hidden) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < FM_NCUBE * E; w += T) {
     EnvS<NA>& s = S[w % E]; int k = w / E;
@@ -229,7 +229,7 @@ FM_HD void xf_compose(const float* Ra, const float* xa, const float* Rb, const f
   st3(xo, x);
 }
 template <int NA, int E>
-FM_HD void ph_arm_local(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_arm_local(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
@@ -254,7 +254,7 @@ FM_HD void ph_arm_local(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 }
 // one scan round: dst_b = (b - dist >= 1 ? src_{b-dist} o src_b : src_b) for chain bodies 1..8; plates are carried through
 template <int NA, int E>
-FM_HD void ph_arm_scan(EnvS<NA>* S, int tid, int T, int dist, bool to_body) {
+FM_PH void ph_arm_scan(EnvS<NA>* S, int tid, int T, int dist, bool to_body) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < NA * (FM_NARMBODY - 1) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / (FM_NARMBODY - 1), b = 1 + ab % (FM_NARMBODY - 1);
@@ -270,7 +270,7 @@ FM_HD void ph_arm_scan(EnvS<NA>* S, int tid, int T, int dist, bool to_body) {
 // After the rounds (dist 1 -> body, 2 -> d_L, 4 -> body) bodies 1..8 are final in body_R and the plates' locals sit in body_R
 // as well (carried), so they are first copied back by the caller's last round; here they are composed in place via registers.
 template <int NA, int E>
-FM_HD void ph_arm_plates(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_arm_plates(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < NA * 2 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ap = w / E; int a = ap / 2, b = 9 + ap % 2;
@@ -285,7 +285,7 @@ FM_HD int chain_hi(int b) { return b < 7 ? b : 7; }
 // Newton-Euler forward pass in ONE interval: lane = (env, arm, body) walks its own ancestor chain with running angular
 // velocity, angular bias acceleration and origin bias acceleration (no cross-lane dependency; <= 8 links).
 template <int NA, int E>
-FM_HD void ph_arm_vel(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_arm_vel(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
@@ -310,7 +310,7 @@ FM_HD void ph_arm_vel(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // final kinematics only (gripper sites after the last sub-step): same scan without the velocity passes
 // phase: per-body quantities (parallel): COM offset, world inertia, composite init, NE body wrench, cluster centre
 template <int NA, int E>
-FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * FM_NARMBODY * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / FM_NARMBODY, b = ab % FM_NARMBODY;
@@ -359,7 +359,7 @@ FM_HD void ph_arm_body(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // (lane = (env, arm, body); subtree of chain body b is b+1..10, of the gripper base the two plates).  Reads the per-body
 // values written by ph_arm_body (d_comp0, d_f0, d_n0) and writes the accumulated ones (d_comp, d_f, d_n): one interval.
 template <int NA, int E>
-FM_HD void ph_arm_bwd(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_arm_bwd(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < NA * (FM_NARMBODY - 1) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ab = w / E; int a = ab / (FM_NARMBODY - 1), b = 1 + ab % (FM_NARMBODY - 1);
@@ -390,7 +390,7 @@ FM_HD void ph_arm_bwd(EnvS<NA>* S, int tid, int T) {
 
 // phase: mass matrix entries M_ij (parallel over 45 pairs per arm) from composite inertias (CRBA)
 template <int NA, int E>
-FM_HD void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * 45 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ap = w / E; int a = ap / 45, pr = ap % 45;
@@ -430,7 +430,7 @@ FM_HD void ph_arm_M(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // L[i][k] = (A[i][k] - sum_{j<k} L[i][j] L[k][j]) / L[k][k]; the pivot is recomputed by every lane (k MACs), so an interval
 // has no intra-interval dependency.
 template <int NA, int E, int K>
-FM_HD void ph_arm_chol_col(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_arm_chol_col(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   constexpr int ROWS = 9 - K;
   for (int w = tid; w < NA * 2 * ROWS * E; w += T) {
@@ -464,7 +464,7 @@ FM_HD void chol9_solve(const float* L, const float* dg, float* x) {
 
 // phase: explicit inverse, one column per thread
 template <int NA, int E>
-FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < NA * 9 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ac = w / E; int a = ac / 9, c = ac % 9;
@@ -482,7 +482,7 @@ FM_HD void ph_arm_minv(EnvS<NA>* S, int tid, int T) {
 // matrix-vector products per dof instead of a serial 9x9 triangular solve on one lane per arm (that lane set the length of the
 // integration interval: 9.5 % of the sub-step spent waiting for it, profiles/r2d).
 template <int NA, int E>
-FM_HD void ph_arm_winv(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_arm_winv(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < NA * 9 * E; w += T) {
     EnvS<NA>& s = S[w % E]; int ac = w / E; int a = ac / 9, c = ac % 9;
@@ -509,15 +509,20 @@ FM_HD void cluster_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx
 
 struct alignas(8) bnd4 { float x, y, z, r; };   // two 64-bit loads: the env stride is 2 (mod 32) words, not a multiple of 4
 template <int NA, int E>
-FM_HD void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
+FM_PH void ph_broad(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int np = m.n_cluster_pair, s0 = m.cl_sph0;
   // lanes per env; consecutive lanes serve the same env, so that a warp whose envs all keep their cached queue skips the phase
   // (with item w -> env w % E every warp would hold lanes of all E envs and run the pair loop for the few stale ones)
   const int stride = T / E;
   if (tid >= stride * E) return;                         // T need not be a multiple of E: the remainder lanes sit this phase out
+#ifdef FM_BROAD_INTERLEAVED
+  EnvS<NA>& s = S[tid % E];
+  const int l0 = tid / E;
+#else
   EnvS<NA>& s = S[tid / stride];
   const int l0 = tid % stride;
+#endif
 #ifndef FM_BROAD_ALWAYS
   if (!s.broad_stale) return;                            // the cached queue is still a superset of the near pairs
 #endif
@@ -653,30 +658,65 @@ FM_HD void narrow_arm_geom_vs(EnvS<NA>& s, const FmDevModel& m, int a2, int b2, 
   }
 }
 
+// one narrow-phase work item w = (env, queued pair, sub-index j)
 template <int NA, int E>
-FM_HD void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
-  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
+FM_HD void narrow_item(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int w) {
+  EnvS<NA>& s = S[w % E]; int rest = w / E; int qi = rest / FM_NSUB, j = rest % FM_NSUB;
+  int nq = s.nqueue < FmCap<NA>::QUEUE ? s.nqueue : FmCap<NA>::QUEUE;
+  if (qi >= nq) return;
+  unsigned rec = cpairs[s.queue[qi]];
+  int c1 = rec & 255, c2 = (rec >> 8) & 255;
+  int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2], i1 = m.cl_idx[c1], i2 = m.cl_idx[c2];
+  if (k2 == FM_CL_ARM) { narrow_arm_geom_vs(s, m, i2 / FM_NARMBODY, i2 % FM_NARMBODY, j, k1, i1); return; }
+  if (j != 0) return;
+  RawC rc[8]; float RidA[9], RidB[9];
+  if (k1 == FM_CL_PLANE) {
+    if (k2 == FM_CL_CUBE) { float h = m.cube_half[i2]; int n = col_plane_box(ld3(s.cube_x[i2]), s.cube_R[i2], mk3(h, h, h), rc); emit(s, 0, m.cube_geom[i2], pack_side(FM_SIDE_STATIC, 0, 0), pack_side(FM_SIDE_CUBE, i2, 0), false, rc, n); }
+    else if (k2 == FM_CL_BELT) { GeomBox b; get_box(s, m, k2, i2, 0, b, RidB); int n = col_plane_box(b.p, b.R, b.hs, rc); emit(s, 0, b.geom, pack_side(FM_SIDE_STATIC, 0, 0), b.side, false, rc, n); }
+  } else {
+    GeomBox x, y; get_box(s, m, k1, i1, 0, x, RidA); get_box(s, m, k2, i2, 0, y, RidB);
+    pair_box_box(s, x, y, false);
+  }
+}
+template <int NA, int E>
+FM_HD int narrow_total(EnvS<NA>* S) {
   int mq = 0;
   for (int e = 0; e < E; ++e) mq = S[e].nqueue > mq ? S[e].nqueue : mq;
   if (mq > FmCap<NA>::QUEUE) mq = FmCap<NA>::QUEUE;
-  for (int w = tid; w < mq * FM_NSUB * E; w += T) {
-    EnvS<NA>& s = S[w % E]; int rest = w / E; int qi = rest / FM_NSUB, j = rest % FM_NSUB;
-    int nq = s.nqueue < FmCap<NA>::QUEUE ? s.nqueue : FmCap<NA>::QUEUE;
-    if (qi >= nq) continue;
-    unsigned rec = cpairs[s.queue[qi]];
-    int c1 = rec & 255, c2 = (rec >> 8) & 255;
-    int k1 = m.cl_kind[c1], k2 = m.cl_kind[c2], i1 = m.cl_idx[c1], i2 = m.cl_idx[c2];
-    if (k2 == FM_CL_ARM) { narrow_arm_geom_vs(s, m, i2 / FM_NARMBODY, i2 % FM_NARMBODY, j, k1, i1); continue; }
-    if (j != 0) continue;
-    RawC rc[8]; float RidA[9], RidB[9];
-    if (k1 == FM_CL_PLANE) {
-      if (k2 == FM_CL_CUBE) { float h = m.cube_half[i2]; int n = col_plane_box(ld3(s.cube_x[i2]), s.cube_R[i2], mk3(h, h, h), rc); emit(s, 0, m.cube_geom[i2], pack_side(FM_SIDE_STATIC, 0, 0), pack_side(FM_SIDE_CUBE, i2, 0), false, rc, n); }
-      else if (k2 == FM_CL_BELT) { GeomBox b; get_box(s, m, k2, i2, 0, b, RidB); int n = col_plane_box(b.p, b.R, b.hs, rc); emit(s, 0, b.geom, pack_side(FM_SIDE_STATIC, 0, 0), b.side, false, rc, n); }
-    } else {
-      GeomBox x, y; get_box(s, m, k1, i1, 0, x, RidA); get_box(s, m, k2, i2, 0, y, RidB);
-      pair_box_box(s, x, y, false);
-    }
+  return mq * FM_NSUB * E;
+}
+// the block's narrow-phase work counter lives in the first env's padding word (reset by ph_clear)
+template <int NA> FM_HD int* narrow_counter(EnvS<NA>* S) { return &S[0].pad_[0]; }
+
+// Narrow phase.  On the GPU the items are handed out in chunks of 32 from a block-wide counter, so that BOTH warp groups of
+// fm_derive work on them: group B from the start, group A as soon as its factorisation intervals are done (it used to wait at
+// the join for a third of the sub-step while four warps walked the queue alone).  Contact emission is order-independent (atomic
+// slots, ranked afterwards).  The host-compiled test build runs the same items in a static loop.
+template <int NA, int E>
+FM_PH void ph_narrow_steal(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int lane) {
+#if defined(__CUDA_ARCH__)
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
+  const int total = narrow_total<NA, E>(S);
+  int* cnt = narrow_counter<NA>(S);
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cnt, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) break;
+    if (base + lane < total) narrow_item<NA, E>(S, m, cpairs, base + lane);
+    __syncwarp();
   }
+#endif
+}
+template <int NA, int E>
+FM_PH void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
+  FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
+#if defined(__CUDA_ARCH__) && !defined(FM_NARROW_STATIC)
+  ph_narrow_steal<NA, E>(S, m, cpairs, tid & 31);
+#else
+  const int total = narrow_total<NA, E>(S);
+  for (int w = tid; w < total; w += T) narrow_item<NA, E>(S, m, cpairs, w);
+#endif
 }
 
 // =====================================================================================================================
@@ -880,7 +920,7 @@ FM_HDN void ph_contact_setup(EnvS<NA>* S, const FmDevModel& m, const int* __rest
 
 // phase: arm-local rows (thread per arm): joint equality q_l - q_r = 0 and joint limits
 template <int NA, int E>
-FM_HD void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < NA * E; w += T) {
     EnvS<NA>& s = S[w % E]; int a = w / E;
@@ -924,7 +964,7 @@ FM_HD void ph_arm_rows(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // contact couples two dynamic nodes (cube-cube, cube-arm, arm-arm), so every node is its own island and the per-island
 // contact lists are built fully in parallel (ph_island_lists).  Otherwise one thread per env runs a union-find first.
 template <int NA, int E>
-FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_island_union(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < E; w += T) {
@@ -948,7 +988,7 @@ FM_HD void ph_island_union(EnvS<NA>* S, int tid, int T) {
   }
 }
 template <int NA, int E>
-FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_island_lists(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < (FmCap<NA>::CON + NN + 1) * E; w += T) {
@@ -975,7 +1015,7 @@ FM_HD void ph_island_lists(EnvS<NA>* S, int tid, int T) {
 // every lane owns one cube (6 rows of acc) or one arm dof and adds Minv J^T f of the previous solve's forces for the contacts /
 // arm rows that touch it, in ascending contact order (fixed order: run-to-run determinism).
 template <int NA, int E>
-FM_HD void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int per = 1 + FM_NCUBE + 9 * NA;
   for (int w = tid; w < per * E; w += T) {
@@ -1124,7 +1164,7 @@ FM_HD float arm_rows_visit(EnvS<NA>& s, int a, int mode) {
 
 // phase: convergence check of the warm start, one lane per contact (evaluation only; nothing another lane reads is written)
 template <int NA, int E>
-FM_HD void ph_check(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_check(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < FmCap<NA>::CON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
@@ -1282,8 +1322,8 @@ FM_HD void island_pgs_sweeps(EnvS<NA>& s, const FmDevModel& m, int node, int c0,
 // contacts (grasps, crashes, cube on cube) are only MARKED here (bit 8 + node of need_union) and solved in the next interval by a
 // whole warp each (ph_big_islands).  What is left (a lone arm's limit rows) is swept here.
 #define FM_BIG_BIT(node) (1 << (8 + (node)))
-template <int NA, int E>
-FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
+template <int NA, int E, bool BIGN>
+FM_PH void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int NN = EnvS<NA>::NNODE;
   for (int w = tid; w < NN * E; w += T) {
@@ -1309,9 +1349,8 @@ FM_HD void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
       FM_DBG(fm_dbg_sat[300]++; fm_dbg_sat[301] += solved;)
     }
     if (solved) continue;
-#ifndef FM_NO_BIG_NEWTON
-    if ((has_arm && c1 > c0) || !alone) { FM_ATOMIC_OR(&s.need_union, FM_BIG_BIT(node)); continue; }   // a warp takes it (ph_big_islands)
-#endif
+    // a warp takes the stiff islands (an arm with contacts: 32 sweeps would not converge them); cube-on-cube islands converge in a few sweeps
+    if (BIGN && has_arm && c1 > c0) { FM_ATOMIC_OR(&s.need_union, FM_BIG_BIT(node)); continue; }
     island_pgs_sweeps(s, m, node, c0, c1, has_arm, single_row, inner, tol);
   }
 }
@@ -1423,20 +1462,21 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
   B.c0 = s.isl_start[root]; B.nc = s.isl_start[root + 1] - B.c0;
   const int NU = B.NU, nc = B.nc, nrows = 4 * nc + B.nrow_arm;
   if (NU > FM_BIG_NU || nc > FM_BIG_NC || nc + B.nrow_arm > 32 || nrows > 128) return false;
-  // scratch: H (packed lower triangle, 300), g (24), a (24) in the dead Newton-Euler buffers; staging + bit sets in the raw keys
-  B.H = &s.d_f[0][0][0]; B.g = B.H + 300; B.a = B.g + 24;
+  // scratch.  H: packed lower triangle of the (NU + 1) x (NU + 1) matrix [H g; g^T .] — lane i owns row i, the right-hand side is
+  // row NU, so the forward substitution falls out of the factorisation; a: NU accelerations (Jacobi scale factors meanwhile).
+  // Both sit in the dead Newton-Euler buffers (d_f, d_n, d_comp: 352 floats); the contact staging and the bit sets in the raw keys.
+  B.H = &s.d_f[0][0][0]; B.g = B.H + tri(NU, 0); B.a = B.H + 326;
   float* rb = reinterpret_cast<float*>(&s.raw_key[0]);
   B.Jc = rb; B.Wg = rb + 72; B.act = reinterpret_cast<unsigned*>(rb + 81); B.prev = B.act + 4; B.chg = reinterpret_cast<int*>(B.prev + 4);
-  const int NH = NU * (NU + 1) / 2;
   L.stage([&](int lane) {
     if (lane < NU) { int ni, q; B.unk(lane, ni, q); B.a[lane] = s.acc[B.acc_index(ni, q)]; }
     if (lane < 4) { B.act[lane] = 0u; B.prev[lane] = 0xFFFFFFFFu; }
+    if (lane == 0) *B.chg = 0;
   });
   bool ok = false;
   for (int it = 0; it < 7; ++it) {
     FM_DBG(fm_dbg_sat[331]++;)
     // ---- active set at the current a: one lane per contact (4 rows) or per arm row
-    L.stage([&](int lane) { if (lane < 4) B.act[lane] = 0u; if (lane == 0) *B.chg = 0; });
     L.stage([&](int lane) {
       if (lane < nc) {
         const int c = s.isl_list[B.c0 + lane];
@@ -1471,31 +1511,51 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
       bool same = true;
       for (int w = 0; w < 4; ++w) same = same && B.act[w] == B.prev[w];
       float cg; memcpy(&cg, B.chg, 4);
-      L.sync();                                               // every lane has read act / prev before the next stage rewrites them
+      L.sync();                                               // every lane has read act / prev / chg before the next stage rewrites them
       if (it > 0 && (same || cg < tol)) { ok = true; break; }
       if (it == 6) break;
     }
-    // ---- assemble H = M + sum_active J^T J / R and g = M a0 + sum_active J^T aref / R
+    // ---- rows of [H g]: the nodes' inertia blocks, M a0, and the arm-local rows (one or two non-zeros each); lane i owns row i
     L.stage([&](int lane) {
-      for (int idx = lane; idx < NH; idx += 32) B.H[idx] = 0.f;
-      if (lane < NU) {
-        int ni, q; B.unk(lane, ni, q);
-        const int nd = B.nodes[ni];
-        B.g[lane] = nd < FM_NCUBE ? (q == 2 ? -m.g / m.cube_invm[nd] : 0.f) : arm_qfrc(s, m, nd - FM_NCUBE, q);
-      }
       if (lane < 4) B.prev[lane] = B.act[lane];
-    });
-    L.stage([&](int lane) {      // the nodes' inertia blocks
-      for (int idx = lane; idx < NH; idx += 32) {
-        int i = 0; while ((i + 1) * (i + 2) / 2 <= idx) ++i;
-        const int j = idx - i * (i + 1) / 2;
-        int ni, qi, nj, qj; B.unk(i, ni, qi); B.unk(j, nj, qj);
-        if (ni != nj) continue;
-        const int nd = B.nodes[ni];
-        if (nd < FM_NCUBE) { if (qi == qj) B.H[idx] = qi < 3 ? 1.f / m.cube_invm[nd] : 1.f / m.cube_invI[nd]; }
-        else B.H[idx] = s.M[nd - FM_NCUBE][tri(qi, qj)];
+      if (lane == 0) *B.chg = 0;
+      if (lane > NU) return;
+      float* row = B.H + tri(lane, 0);
+      if (lane == NU) {                                      // the right-hand side row: g_j = (M a0)_j (+ the active arm rows' J^T aref / R)
+        for (int j = 0; j < NU; ++j) {
+          int nj, qj; B.unk(j, nj, qj);
+          const int nd = B.nodes[nj];
+          row[j] = nd < FM_NCUBE ? (qj == 2 ? -m.g / m.cube_invm[nd] : 0.f) : arm_qfrc(s, m, nd - FM_NCUBE, qj);
+        }
+        row[NU] = 0.f;
+      } else {
+        int ni, qi; B.unk(lane, ni, qi);
+        const int nd = B.nodes[ni], o = B.off[ni];
+        for (int j = 0; j <= lane; ++j) {
+          float v = 0.f;
+          if (j >= o) v = nd < FM_NCUBE ? (j == lane ? (qi < 3 ? 1.f / m.cube_invm[nd] : 1.f / m.cube_invI[nd]) : 0.f) : s.M[nd - FM_NCUBE][tri(qi, j - o)];
+          row[j] = v;
+        }
+      }
+      for (int ni = 0; ni < B.nnode; ++ni) {               // arm rows touching this lane's row
+        if (B.nodes[ni] < FM_NCUBE) continue;
+        const int a = B.nodes[ni] - FM_NCUBE, o = B.off[ni];
+        for (int r = 0; r < s.arow_n[a]; ++r) {
+          const int bit = 4 * nc + B.arm_row0[ni] + r;
+          if (!((B.act[bit >> 5] >> (bit & 31)) & 1u)) continue;
+          const int code = s.arow_code[a][r]; const float D = 1.f / s.arow_R[a][r], ar = s.arow_aref[a][r];
+          if (code & 0x1000) {
+            const int i7 = o + 7, i8 = o + 8;
+            if (lane == i7) row[i7] += D; else if (lane == i8) { row[i8] += D; row[i7] -= D; }
+            else if (lane == NU) { row[i7] += D * ar; row[i8] -= D * ar; }
+          } else {
+            const int d = o + (code & 255); const float sg = (code >> 8) ? -1.f : 1.f;
+            if (lane == d) row[d] += D; else if (lane == NU) row[d] += sg * D * ar;
+          }
+        }
       }
     });
+    // ---- contacts: H += J_c^T W_c J_c, g += J_c^T g_c, one contact after the other (columns staged by the lanes, W_c by lane 31)
     for (int ci = 0; ci < nc; ++ci) {
       const int c = s.isl_list[B.c0 + ci];
       L.stage([&](int lane) {
@@ -1517,70 +1577,51 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
         }
       });
       L.stage([&](int lane) {
-        const float W00 = B.Wg[0], W11 = B.Wg[1], W22 = B.Wg[2], W01 = B.Wg[3], W02 = B.Wg[4];
-        if (lane < NU) B.g[lane] += B.Jc[lane] * B.Wg[6] + B.Jc[24 + lane] * B.Wg[7] + B.Jc[48 + lane] * B.Wg[8];
-        for (int idx = lane; idx < NH; idx += 32) {
-          int i = 0; while ((i + 1) * (i + 2) / 2 <= idx) ++i;
-          const int j = idx - i * (i + 1) / 2;
-          const float i0 = B.Jc[i], i1 = B.Jc[24 + i], i2 = B.Jc[48 + i];
-          if (i0 == 0.f && i1 == 0.f && i2 == 0.f) continue;
-          const float j0 = B.Jc[j], j1 = B.Jc[24 + j], j2 = B.Jc[48 + j];
-          const float t0 = W00 * j0 + W01 * j1 + W02 * j2, t1 = W01 * j0 + W11 * j1, t2 = W02 * j0 + W22 * j2;   // the pyramid has no (t1, t2) term
-          B.H[idx] += i0 * t0 + i1 * t1 + i2 * t2;
+        if (lane > NU) return;
+        float t0, t1, t2;
+        if (lane == NU) { t0 = B.Wg[6]; t1 = B.Wg[7]; t2 = B.Wg[8]; }           // g row: J_c^T g_c
+        else {
+          const float i0 = B.Jc[lane], i1 = B.Jc[24 + lane], i2 = B.Jc[48 + lane];
+          if (i0 == 0.f && i1 == 0.f && i2 == 0.f) return;
+          const float W00 = B.Wg[0], W11 = B.Wg[1], W22 = B.Wg[2], W01 = B.Wg[3], W02 = B.Wg[4];   // the pyramid has no (t1, t2) term
+          t0 = W00 * i0 + W01 * i1 + W02 * i2; t1 = W01 * i0 + W11 * i1; t2 = W02 * i0 + W22 * i2;
         }
+        float* row = B.H + tri(lane, 0);
+        const int jn = lane == NU ? NU : lane + 1;
+        for (int j = 0; j < jn; ++j) row[j] += t0 * B.Jc[j] + t1 * B.Jc[24 + j] + t2 * B.Jc[48 + j];
       });
     }
-    L.stage([&](int lane) {      // arm-local rows (one or two non-zeros each): lane 0, in row order
-      if (lane != 0) return;
-      for (int ni = 0; ni < B.nnode; ++ni) {
-        if (B.nodes[ni] < FM_NCUBE) continue;
-        const int a = B.nodes[ni] - FM_NCUBE, o = B.off[ni];
-        for (int r = 0; r < s.arow_n[a]; ++r) {
-          const int bit = 4 * nc + B.arm_row0[ni] + r;
-          if (!((B.act[bit >> 5] >> (bit & 31)) & 1u)) continue;
-          const int code = s.arow_code[a][r]; const float D = 1.f / s.arow_R[a][r], ar = s.arow_aref[a][r];
-          if (code & 0x1000) {
-            const int i7 = o + 7, i8 = o + 8;
-            B.H[tri(i7, i7)] += D; B.H[tri(i8, i8)] += D; B.H[tri(i8, i7)] -= D;
-            B.g[i7] += D * ar; B.g[i8] -= D * ar;
-          } else {
-            const int d = o + (code & 255); const float sg = (code >> 8) ? -1.f : 1.f;
-            B.H[tri(d, d)] += D; B.g[d] += sg * D * ar;
-          }
-        }
-      }
-    });
-    // ---- Jacobi scaling (the arm's inertias span three decades), Cholesky, two triangular solves: all in place
+    // ---- Jacobi scaling (the arm's inertias span three decades): S = diag(H)^-1/2, [H g] <- S [H g] S
     L.stage([&](int lane) { if (lane < NU) B.a[lane] = rsqrtf(fmaxf(B.H[tri(lane, lane)], 1e-30f)); });
     L.stage([&](int lane) {
-      for (int idx = lane; idx < NH; idx += 32) { int i = 0; while ((i + 1) * (i + 2) / 2 <= idx) ++i; const int j = idx - i * (i + 1) / 2; B.H[idx] *= B.a[i] * B.a[j]; }
-      if (lane < NU) B.g[lane] *= B.a[lane];
+      if (lane > NU) return;
+      float* row = B.H + tri(lane, 0);
+      const float si = lane == NU ? 1.f : B.a[lane];
+      const int jn = lane == NU ? NU : lane + 1;
+      for (int j = 0; j < jn; ++j) row[j] *= si * B.a[j];
     });
+    // ---- left-looking Cholesky, one stage per column, lane i = row i (row NU carries the right-hand side: y = L^-1 g).  The
+    // factor's diagonal goes to dg (the contact staging is dead now): the unfactored H[k][k] must stay readable in this stage
+    float* dg = B.Jc; float* xs = B.Jc + 24;
     for (int k = 0; k < NU; ++k) {
-      L.stage([&](int lane) {      // column k: L[i][k] = H[i][k] / sqrt(H[k][k]) for i >= k
-        const float piv = rsqrtf(fmaxf(B.H[tri(k, k)], 1e-30f));
-        const int i = k + lane;
-        if (i < NU && i > k) B.H[tri(i, k)] *= piv;
-      });
-      L.stage([&](int lane) {      // the pivot itself, then the trailing update
-        if (lane == 0) B.H[tri(k, k)] = sqrtf(fmaxf(B.H[tri(k, k)], 1e-30f));
-        const int n1 = NU - k - 1;
-        for (int e = lane; e < n1 * (n1 + 1) / 2; e += 32) {
-          int ii = 0; while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-          const int jj = e - ii * (ii + 1) / 2;
-          const int i = k + 1 + ii, j = k + 1 + jj;
-          B.H[tri(i, j)] -= B.H[tri(i, k)] * B.H[tri(j, k)];
-        }
+      L.stage([&](int lane) {
+        if (lane < k || lane > NU) return;
+        const float* rk = B.H + tri(k, 0); float* ri = B.H + tri(lane, 0);
+        float piv = rk[k], v = ri[k];
+        for (int j = 0; j < k; ++j) { const float lkj = rk[j]; piv -= lkj * lkj; v -= ri[j] * lkj; }
+        const float rp = rsqrtf(fmaxf(piv, 1e-30f));       // every lane recomputes the pivot from row k's finished part (columns < k)
+        if (lane == k) dg[k] = fmaxf(piv, 1e-30f) * rp; else ri[k] = v * rp;
       });
     }
-    L.stage([&](int lane) {        // forward and backward substitution on lane 0 (24 x 24: ~600 multiply-adds), then un-scale
-      if (lane != 0) return;
-      float y[FM_BIG_NU];
-      for (int i = 0; i < NU; ++i) { float v = B.g[i]; for (int q = 0; q < i; ++q) v -= B.H[tri(i, q)] * y[q]; y[i] = v / B.H[tri(i, i)]; }
-      for (int i = NU - 1; i >= 0; --i) { float v = y[i]; for (int q = i + 1; q < NU; ++q) v -= B.H[tri(q, i)] * y[q]; y[i] = v / B.H[tri(i, i)]; }
-      for (int i = 0; i < NU; ++i) B.g[i] = y[i];
-    });
-    L.stage([&](int lane) { if (lane < NU) B.a[lane] *= B.g[lane]; });
+    // ---- back substitution L^T x = y, column-oriented
+    for (int k = NU - 1; k >= 0; --k) {
+      L.stage([&](int lane) {
+        if (lane > k) return;
+        const float xk = B.g[k] / dg[k];
+        if (lane == k) xs[k] = xk; else B.g[lane] -= B.H[tri(k, lane)] * xk;
+      });
+    }
+    L.stage([&](int lane) { if (lane < NU) B.a[lane] *= xs[lane]; if (lane < 4) B.act[lane] = 0u; });
   }
   FM_DBG(fm_dbg_sat[332] += ok;)
   if (!ok) return false;
@@ -1624,11 +1665,12 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
 
 // phase: one warp per marked island (see ph_pgs); an island the Newton cannot take or settle falls back to the sweeps on one lane
 template <int NA, int E, class Lanes>
-FM_HD void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps, Lanes& L, int inner, float tol) {
+FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps, Lanes& L, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int NN = EnvS<NA>::NNODE;
-  for (int w = warp; w < NN * E; w += nwarps) {
-    EnvS<NA>& s = S[w % E]; const int node = w / E;
+  // all marked islands of one env go to the SAME warp, one after the other: they share the env's scratch (H, g, a, staging)
+  for (int w = warp; w < E; w += nwarps) for (int node = 0; node < NN; ++node) {
+    EnvS<NA>& s = S[w];
     if (!(s.need_union & FM_BIG_BIT(node))) continue;
     FM_DBG(fm_dbg_sat[330]++;)
     const bool ok = island_newton_warp<NA>(s, m, node, L, tol);
@@ -1647,7 +1689,7 @@ FM_HD void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps
 // belt acceleration from this solve's contact forces (fixed summation order: run-to-run determinism).  During the solve the
 // belt dof is held at its smooth acceleration plus the previous sub-step's contact term (the coupling is ~1e-3 of a cube's).
 template <int NA, int E>
-FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   for (int w = tid; w < E; w += T) {
     EnvS<NA>& s = S[w];
@@ -1660,7 +1702,7 @@ FM_HD void ph_belt(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 
 // phase: force-termination statistic on the forces of this solve (base_env.py:226-236; clarification SURVEY.md A.2)
 template <int NA, int E>
-FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_force_check(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < FmCap<NA>::CON * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
@@ -1675,7 +1717,7 @@ FM_HD void ph_force_check(EnvS<NA>* S, int tid, int T) {
 
 // phase: implicitfast velocity update + semi-implicit position integration (mj_implicit, mj_advance) [3P]
 template <int NA, int E>
-FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int per = 1 + FM_NCUBE + 9 * NA;
   for (int w = tid; w < per * E; w += T) {
@@ -1713,6 +1755,21 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       }
       q[3] = qq.w; q[4] = qq.x; q[5] = qq.y; q[6] = qq.z;
     } else {
+#ifdef FM_INTEGRATE_SERIAL
+      const int ad = i - 1 - FM_NCUBE;
+      if (ad % 9 != 0) continue;
+      const int a = ad / 9;
+      float* acc = &s.acc[61 + 9 * a];
+      float y[9];
+      for (int r = 0; r < 9; ++r) { float sum = 0.f; for (int k = 0; k < 9; ++k) sum += s.M[a][r >= k ? tri(r, k) : tri(k, r)] * acc[k]; y[r] = sum; }
+      chol9_solve(s.Li[a], s.chol_d[a][1], y);
+      float* ql = s.arm_qlo(a);
+      for (int r = 0; r < 9; ++r) {
+        s.arm_v[a][r] += h * y[r];
+        float q0 = s.arm_q[a][r], inc = h * s.arm_v[a][r] + ql[r];
+        float nq = q0 + inc; ql[r] = inc - (nq - q0); s.arm_q[a][r] = nq;
+      }
+#else
       // arm dof r: qacc_r = [(M - hD)^-1 M acc]_r; every lane forms y = M acc itself (81 multiply-adds, nine independent sums)
       const int ad = i - 1 - FM_NCUBE; const int a = ad / 9, r = ad % 9;
       const float* acc = &s.acc[61 + 9 * a]; const float* Mp = s.M[a]; const float* Wp = s.Lc[a];
@@ -1732,13 +1789,14 @@ FM_HD void ph_integrate(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
       const float nq = q0 + inc;
       ql[r] = inc - (nq - q0);
       s.arm_q[a][r] = nq;
+#endif
     }
   }
 }
 
 // phase: remember this solve's forces for the next warm start
 template <int NA, int E>
-FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_save_forces(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
   for (int w = tid; w < (FmCap<NA>::CON + NA) * E; w += T) {
     EnvS<NA>& s = S[w % E]; int c = w / E;
@@ -1758,7 +1816,7 @@ FM_HD void ph_save_forces(EnvS<NA>* S, int tid, int T) {
 // start of the step.  Evaluated that way because the recursion stalls in fp32 once its increment falls below half an ulp
 // (1.2e-5 short of a target of 1.0: an idle arm then hangs 1e-5 rad off the reference's pose, tests/ref_cases.py).
 template <int NA, int E>
-FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float pk) {
+FM_PH void ph_ctrl(EnvS<NA>* S, int tid, int T, float pk) {
   FM_ASSUME_SHARED(S);
   const int NU = EnvS<NA>::NU;
   for (int w = tid; w < NU * E; w += T) {
@@ -1768,7 +1826,7 @@ FM_HD void ph_ctrl(EnvS<NA>* S, int tid, int T, float pk) {
   }
 }
 template <int NA, int E>
-FM_HD void ph_clear(EnvS<NA>* S, int tid, int T) {
+FM_PH void ph_clear(EnvS<NA>* S, int tid, int T) {
   FM_ASSUME_SHARED(S);
-  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.ncon = 0; s.need_union = 0; for (int i = 0; i < EnvS<NA>::NNODE; ++i) s.isl_root[i] = i; }
+  for (int w = tid; w < E; w += T) { EnvS<NA>& s = S[w]; s.nraw = 0; s.ncon = 0; s.need_union = 0; s.pad_[0] = 0; for (int i = 0; i < EnvS<NA>::NNODE; ++i) s.isl_root[i] = i; }
 }

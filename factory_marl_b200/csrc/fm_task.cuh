@@ -68,7 +68,7 @@ FM_HD double pcg64_uniform(unsigned long long* st /*hi, lo, inc_hi, inc_lo*/) {
 
 // ---- load / store between HBM (SoA) and shared memory
 template <int NA, int E>
-FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
@@ -133,7 +133,7 @@ FM_HD void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
 
 // the task manager's edits (spawn / hide) become visible to the integrator only after the first derive
 template <int NA, int E>
-FM_HD void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S);
   typedef Lay<NA> L;
   int N = st.n;
@@ -147,7 +147,7 @@ FM_HD void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid,
 
 // ---- action map -> ctrl (clipped to actuator_ctrlrange, base_env.py:255-262)
 template <int NA, int E>
-FM_HD void ph_action(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, const float* act_f,
+FM_PH void ph_action(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, const float* act_f,
                      const int* act_i, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
@@ -198,7 +198,7 @@ FM_HD void ph_action(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg
 
 // ---- save the physical (pre-edit) cube state for the next launch's first derive
 template <int NA, int E>
-FM_HD void ph_store_pre(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_store_pre(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S);
   typedef Lay<NA> L;
   int N = st.n;
@@ -246,7 +246,7 @@ FM_HD void task_reset_state(EnvS<NA>& s, TaskS& t, const FmEnvCfg& cfg) {
 
 // ---- task manager step + reward + termination (thread per env)
 template <int NA, int E>
-FM_HD void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   int N = st.n;
   for (int w = tid; w < E; w += T) {
@@ -370,7 +370,7 @@ FM_HD float obs_value(const EnvS<NA>& s, const TaskS& t, int j) {
 
 // write base observation (_get_state + _process_observation, base_env.py:149-175, environments.py:55-82)
 template <int NA, int E>
-FM_HD void ph_obs(EnvS<NA>* S, TaskS* TS, float* obs, int obs_dim, int n_envs, int env0, int tid, int T, bool only_done) {
+FM_PH void ph_obs(EnvS<NA>* S, TaskS* TS, float* obs, int obs_dim, int n_envs, int env0, int tid, int T, bool only_done) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   const int base = 24 * NA + 130;
   for (int w = tid; w < base * E; w += T) {
@@ -382,7 +382,7 @@ FM_HD void ph_obs(EnvS<NA>* S, TaskS* TS, float* obs, int obs_dim, int n_envs, i
 }
 
 template <int NA, int E>
-FM_HD void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* reward, unsigned char* terminated, int* scores,
+FM_PH void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* reward, unsigned char* terminated, int* scores,
                       unsigned char* flags, float* ep_info, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
@@ -404,7 +404,7 @@ FM_HD void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* rewa
 
 // reset (reset_sim base_env.py:177-198 + TaskManager.reset task_utils.py:146-156) for terminated envs when auto-reset is on
 template <int NA, int E>
-FM_HD void ph_reset_done(EnvS<NA>* S, TaskS* TS, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T, const unsigned char* mask) {
+FM_PH void ph_reset_done(EnvS<NA>* S, TaskS* TS, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T, const unsigned char* mask) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
@@ -421,7 +421,7 @@ FM_HD void ph_reset_done(EnvS<NA>* S, TaskS* TS, const FmEnvCfg& cfg, const FmSt
 }
 
 template <int NA, int E>
-FM_HD void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
@@ -486,7 +486,7 @@ FM_HD void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
 
 // gripper site positions (between_gripper_plates, gripper.xml:43) after the final kinematics
 template <int NA, int E>
-FM_HD void ph_site(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_site(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   for (int w = tid; w < NA * E; w += T) {
     int e = w % E, a = w / E;

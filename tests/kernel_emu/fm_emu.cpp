@@ -47,6 +47,8 @@ struct fm_handle {
 
 template <int NA, int E, int TW = E>
 static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
+  // same rule as the library: the IK-driven classes run the variant with the big-island Newton (here for every block shape)
+  const bool bign = h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1;
   HostRun run{32 * TW};
   size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS)) + 64;
   if (h->smem.size() < need) h->smem.resize(need);
@@ -54,7 +56,8 @@ static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
   for (int b = 0; b < nblk; ++b) {
     memset(h->smem.data(), 0, need);
     EnvS<NA>* S = (EnvS<NA>*)h->smem.data(); TaskS* TS = (TaskS*)(S + E);
-    fm_block_step<NA, E, TW>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
+    if (bign) fm_block_step<NA, E, TW, true>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
+    else fm_block_step<NA, E, TW, false>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
   }
 }
 static void dispatch(fm_handle* h, const FmStepArgs& ar) {
