@@ -84,7 +84,7 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
         sub([&](int tid) { ph_arm_minv<NA, E>(S, tid, TA); ph_arm_rows<NA, E>(S, m, tid, TA); });   // the arm-local rows need no contact
 #ifndef FM_INTEGRATE_SERIAL
         sub([&](int tid) { ph_arm_winv<NA, E>(S, tid, TA);
-#if !defined(FM_NARROW_STATIC)
+#if defined(FM_NARROW_STEAL)
                            if (WB > 0) ph_narrow_steal<NA, E>(S, m, cpairs, tid & 31);   // group A is done: help group B with the narrow phase
 #endif
         });                                       // Lc is dead now: (M - hD)^-1 goes there

@@ -688,10 +688,10 @@ FM_HD int narrow_total(EnvS<NA>* S) {
 // the block's narrow-phase work counter lives in the first env's padding word (reset by ph_clear)
 template <int NA> FM_HD int* narrow_counter(EnvS<NA>* S) { return &S[0].pad_[0]; }
 
-// Narrow phase.  On the GPU the items are handed out in chunks of 32 from a block-wide counter, so that BOTH warp groups of
-// fm_derive work on them: group B from the start, group A as soon as its factorisation intervals are done (it used to wait at
-// the join for a third of the sub-step while four warps walked the queue alone).  Contact emission is order-independent (atomic
-// slots, ranked afterwards).  The host-compiled test build runs the same items in a static loop.
+// Narrow phase.  Optional (-DFM_NARROW_STEAL): the items are handed out in chunks of 32 from a block-wide counter, so that BOTH
+// warp groups of fm_derive work on them (group A joins when its factorisation intervals are done).  Measured 5 % SLOWER than the
+// static loop on the bench workload (profiles/README r2l): the interval is as long as its one general box-box SAT item, not as
+// its item count.  Contact emission is order-independent either way (atomic slots, ranked afterwards).
 template <int NA, int E>
 FM_PH void ph_narrow_steal(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int lane) {
 #if defined(__CUDA_ARCH__)
@@ -711,7 +711,7 @@ FM_PH void ph_narrow_steal(EnvS<NA>* S, const FmDevModel& m, const unsigned int*
 template <int NA, int E>
 FM_PH void ph_narrow(EnvS<NA>* S, const FmDevModel& m, const unsigned int* __restrict__ cpairs, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
-#if defined(__CUDA_ARCH__) && !defined(FM_NARROW_STATIC)
+#if defined(__CUDA_ARCH__) && defined(FM_NARROW_STEAL)
   ph_narrow_steal<NA, E>(S, m, cpairs, tid & 31);
 #else
   const int total = narrow_total<NA, E>(S);
@@ -1623,7 +1623,7 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
     }
     L.stage([&](int lane) { if (lane < NU) B.a[lane] *= xs[lane]; if (lane < 4) B.act[lane] = 0u; });
   }
-  FM_DBG(fm_dbg_sat[332] += ok;)
+  FM_DBG(fm_dbg_sat[332] += ok; fm_dbg_sat[340 + (nc < 24 ? nc : 24)]++; fm_dbg_sat[370 + NU]++;)
   if (!ok) return false;
   // ---- accept: accelerations, forces f = max(-x, 0) / R of the final a, belt projections
   L.stage([&](int lane) {
@@ -1675,6 +1675,7 @@ FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps
     FM_DBG(fm_dbg_sat[330]++;)
     const bool ok = island_newton_warp<NA>(s, m, node, L, tol);
     if (!ok) {
+      FM_DBG(fm_dbg_sat[333]++; long long sw0 = fm_dbg_sweeps;)
       L.stage([&](int lane) {
         if (lane != 0) return;
         const int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
@@ -1682,6 +1683,7 @@ FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps
         for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
         island_pgs_sweeps(s, m, node, c0, c1, has_arm, false, inner, tol);
       });
+      FM_DBG(fm_dbg_sat[334] += fm_dbg_sweeps - sw0;)
     }
   }
 }

@@ -32,7 +32,7 @@ def _newer(target: str, deps) -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = SO_PATH, objdir: str | None = None) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = SO_PATH, objdir: str | None = None, only=None) -> str:
     """nvcc cross-compiles for sm_100a without a GPU (used by __graft_entry__.build()).  One object per .cu, compiled in
     parallel: the fused step kernel is fully inlined (~50 k SASS lines per block shape), so every shape is its own
     translation unit.  extra_flags / out / objdir: kernel-variant experiments (tools/ab_variant.py)."""
@@ -42,6 +42,9 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str =
     os.makedirs(bdir, exist_ok=True)
     objs, jobs = [], []
     for cu, deps in _DEPS.items():
+        if only is not None and cu not in only:             # kernel-variant experiments: every other object comes from the main build
+            objs.append(os.path.join(src, "build", cu.replace(".cu", ".o")))
+            continue
         obj = os.path.join(bdir, cu.replace(".cu", ".o"))
         if force or _newer(obj, [os.path.join(src, d) for d in deps]):
             jobs.append(["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
