@@ -202,9 +202,12 @@ FM_HDN int col_box_box(f3 p1, const float* R1, f3 A, f3 p2, const float* R2, f3 
 // the separating-axis search of col_box_box always selects the big box's +z face (see tests: fm_emu_check_box_on_face),
 // no clipping happens, and the contacts are the vertices of the incident face below the surface, in the same order.
 // `big_is_1`: the big box is geom1 (normal +z) or geom2 (normal -z).  Returns -1 when the fast path does not apply.
-FM_HD int col_box_on_face(f3 pb, f3 hb, f3 pc, const float* Rc, f3 hc, bool big_is_1, RawC* out) {
+// `zlo`: low-order part of the small box's z position (compensated integration, EnvS::cube_qlo): the penetration of a resting cube
+// (2.3e-6 m) is resolved below the 1.2e-7 m grid of a float near z = 1.13.
+// `top_hi`, `top_lo`: the big box's top face height as a float pair (FmDevModel::belt_top / sbox_top); NaN = use pb.z + hb.z.
+FM_HD int col_box_on_face(f3 pb, f3 hb, f3 pc, const float* Rc, f3 hc, bool big_is_1, RawC* out, float zlo = 0.f, float top_hi = -1.f, float top_lo = 0.f) {
   float r = norm3(hc);
-  float top = pb.z + hb.z;
+  float top = top_hi >= 0.f ? top_hi : pb.z + hb.z;
   // horizontal half-extents of the small box (exact projection of its vertices on the big box's x / y axes)
   float ex = fabsf(Rc[0]) * hc.x + fabsf(Rc[1]) * hc.y + fabsf(Rc[2]) * hc.z, ey = fabsf(Rc[3]) * hc.x + fabsf(Rc[4]) * hc.y + fabsf(Rc[5]) * hc.z;
   if (!(fminf(hb.x, hb.y) >= 0.25f) || pc.z < top || fabsf(pc.x - pb.x) + ex * 1.0001f > hb.x || fabsf(pc.y - pb.y) + ey * 1.0001f > hb.y) return -1;
@@ -217,15 +220,18 @@ FM_HD int col_box_on_face(f3 pb, f3 hb, f3 pc, const float* Rc, f3 hc, bool big_
     if (-dd < mn) { mn = -dd; iax = k; isg = -1.f; }
   }
   int i1 = (iax + 1) % 3, i2 = (iax + 2) % 3;
-  f3 fc = pc + rcol(Rc, iax) * (isg * comp3(hc, iax));
+  f3 fv = rcol(Rc, iax) * (isg * comp3(hc, iax));
+  f3 fc = pc + fv;
   f3 e1 = rcol(Rc, i1) * comp3(hc, i1), e2 = rcol(Rc, i2) * comp3(hc, i2);
   f3 rc = mk3(pb.x, pb.y, top);
   f3 n = big_is_1 ? nr : nr * -1.0f;
+  const float zc = (pc.z - top) + (zlo - top_lo);  // exact difference of two nearby floats, plus what the two float values dropped
   int cnt = 0;
   for (int k = 0; k < 4; ++k) {
-    f3 q = fc + e1 * ((k == 0 || k == 3) ? 1.f : -1.f) + e2 * ((k < 2) ? 1.f : -1.f);
+    const float s1 = (k == 0 || k == 3) ? 1.f : -1.f, s2 = (k < 2) ? 1.f : -1.f;
+    f3 q = fc + e1 * s1 + e2 * s2;
     f3 dq = q - rc;
-    float hgt = dq.z;
+    float hgt = zc + (fv.z + e1.z * s1 + e2.z * s2);   // height of the vertex above the face from small terms only
     if (hgt > 0.f) continue;
     out[cnt].pos = rc + mk3(1, 0, 0) * dq.x + mk3(0, 1, 0) * dq.y + nr * (hgt * 0.5f);
     out[cnt].n = n; out[cnt].dist = hgt;

@@ -50,12 +50,14 @@ inline void fm_build_host_model(const void* blob, size_t n, FmHostModel& H) {
   const int32_t* sbg = I(blob, n, "g_sbox_geom");
   for (int i = 0; i < m.n_sbox; ++i) {
     for (int k = 0; k < 3; ++k) { m.sbox_pos[i][k] = (float)sb[15 * i + k]; m.sbox_half[i][k] = (float)sb[15 * i + 12 + k]; }
+    { const double top = sb[15 * i + 2] + sb[15 * i + 14]; m.sbox_top[i][0] = (float)top; m.sbox_top[i][1] = (float)(top - (double)(float)top); }
     for (int k = 0; k < 9; ++k) m.sbox_R[i][k] = (float)sb[15 * i + 3 + k];
     m.sbox_geom[i] = sbg[i]; m.sbox_class[i] = gclass[sbg[i]];
     { const float* R = m.sbox_R[i]; m.sbox_aligned[i] = (R[0] == 1.f && R[4] == 1.f && R[8] == 1.f && R[1] == 0.f && R[2] == 0.f && R[3] == 0.f && R[5] == 0.f && R[6] == 0.f && R[7] == 0.f) ? 1 : 0; }
   }
   const double* bl = D(blob, n, "g_belt");
   for (int k = 0; k < 3; ++k) { m.belt_pos[k] = (float)bl[k]; m.belt_half[k] = (float)bl[3 + k]; }
+  { const double top = bl[2] + bl[5]; m.belt_top[0] = (float)top; m.belt_top[1] = (float)(top - (double)(float)top); }
   m.belt_mass = (float)bl[6]; m.belt_damp = (float)bl[7]; m.belt_kv = (float)bl[8]; m.belt_invw = (float)bl[9];
   m.belt_geom = I(blob, n, "g_belt_geom")[0]; m.belt_class = gclass[m.belt_geom];
   const double* cu = D(blob, n, "g_cube");

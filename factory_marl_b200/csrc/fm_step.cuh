@@ -578,13 +578,14 @@ FM_HD void emit(EnvS<NA>& s, int g1, int g2, int side1, int side2, bool armgeom,
   }
 }
 
-struct GeomBox { f3 p; const float* R; f3 hs; int geom, side, cls, axis_aligned; };
+struct GeomBox { f3 p; const float* R; f3 hs; int geom, side, cls, axis_aligned; float zlo, top_hi, top_lo; };
 
 template <int NA>
 FM_HD void get_box(const EnvS<NA>& s, const FmDevModel& m, int kind, int idx, int sub, GeomBox& g, float* Rid) {
-  if (kind == FM_CL_SBOX) { g.p = ld3(m.sbox_pos[idx]); g.R = m.sbox_R[idx]; g.hs = ld3(m.sbox_half[idx]); g.geom = m.sbox_geom[idx]; g.side = pack_side(FM_SIDE_STATIC, 0, 0); g.cls = m.sbox_class[idx]; g.axis_aligned = m.sbox_aligned[idx]; }
-  else if (kind == FM_CL_BELT) { cluster_box(s, m, kind, idx, g.p, g.R, g.hs, Rid); g.geom = m.belt_geom; g.side = pack_side(FM_SIDE_BELT, 0, 0); g.cls = m.belt_class; g.axis_aligned = 1; }
-  else if (kind == FM_CL_CUBE) { g.p = ld3(s.cube_x[idx]); g.R = s.cube_R[idx]; float h = m.cube_half[idx]; g.hs = mk3(h, h, h); g.geom = m.cube_geom[idx]; g.side = pack_side(FM_SIDE_CUBE, idx, 0); g.cls = m.cube_class; g.axis_aligned = 0; }
+  g.zlo = 0.f; g.top_hi = -1.f; g.top_lo = 0.f;
+  if (kind == FM_CL_SBOX) { g.top_hi = m.sbox_top[idx][0]; g.top_lo = m.sbox_top[idx][1]; g.p = ld3(m.sbox_pos[idx]); g.R = m.sbox_R[idx]; g.hs = ld3(m.sbox_half[idx]); g.geom = m.sbox_geom[idx]; g.side = pack_side(FM_SIDE_STATIC, 0, 0); g.cls = m.sbox_class[idx]; g.axis_aligned = m.sbox_aligned[idx]; }
+  else if (kind == FM_CL_BELT) { g.top_hi = m.belt_top[0]; g.top_lo = m.belt_top[1]; cluster_box(s, m, kind, idx, g.p, g.R, g.hs, Rid); g.geom = m.belt_geom; g.side = pack_side(FM_SIDE_BELT, 0, 0); g.cls = m.belt_class; g.axis_aligned = 1; }
+  else if (kind == FM_CL_CUBE) { g.p = ld3(s.cube_x[idx]); g.R = s.cube_R[idx]; float h = m.cube_half[idx]; g.hs = mk3(h, h, h); g.geom = m.cube_geom[idx]; g.side = pack_side(FM_SIDE_CUBE, idx, 0); g.cls = m.cube_class; g.axis_aligned = 0; g.zlo = s.cube_qlo[idx][2]; }
   else {  // arm body box `sub`
     int a = idx / FM_NARMBODY, b = idx % FM_NARMBODY;
     g.R = s.body_R[a][b]; g.p = ld3(s.body_x[a][b]) + rmul(g.R, ld3(m.abox_pos[sub])); g.hs = ld3(m.abox_half[sub]);
@@ -597,7 +598,7 @@ FM_HD void pair_box_box(EnvS<NA>& s, const GeomBox& x, const GeomBox& y, bool ar
   const GeomBox& g1 = x.geom < y.geom ? x : y; const GeomBox& g2 = x.geom < y.geom ? y : x;
   if (g1.axis_aligned && !g2.axis_aligned) {      // small box on the top face of a big axis-aligned box (belt, table): fast path.
     RawC rf[4];                                   // Only with the big box as geom1: on exact face-axis ties the general routine
-    int nf = col_box_on_face(g1.p, g1.hs, g2.p, g2.R, g2.hs, true, rf);   // prefers box 1's face, which must be the big one.
+    int nf = col_box_on_face(g1.p, g1.hs, g2.p, g2.R, g2.hs, true, rf, g2.zlo, g1.top_hi, g1.top_lo);   // prefers box 1's face, which must be the big one.
     if (nf >= 0) { FM_DBG(fm_dbg_cnt[27]++;) emit(s, g1.geom, g2.geom, g1.side, g2.side, armgeom, rf, nf); return; }
   }
   if (far_sphere_box(g2.p, norm3(g2.hs), g1.p, g1.R, g1.hs) || far_sphere_box(g1.p, norm3(g1.hs), g2.p, g2.R, g2.hs)) { FM_DBG(fm_dbg_cnt[28]++;) return; }

@@ -36,6 +36,9 @@ struct FmDevModel {
   // static boxes (world frame): pos, rot (row-major), half size, contact class, geom id
   float sbox_pos[FM_MAX_SBOX][3], sbox_R[FM_MAX_SBOX][9], sbox_half[FM_MAX_SBOX][3];
   int sbox_geom[FM_MAX_SBOX], sbox_class[FM_MAX_SBOX], sbox_aligned[FM_MAX_SBOX];
+  // top face height (pos.z + half.z) of the axis-aligned big boxes as float pairs (hi = nearest float, lo = remainder of the fp64
+  // sum): 1.05f + 0.04f rounds to 1.0899999, 8.6e-8 below the belt's real top — a third of a resting cube's float grid
+  float sbox_top[FM_MAX_SBOX][2], belt_top[2];
   // belt (conveyor_belt.xml:4-11)
   float belt_pos[3], belt_half[3], belt_mass, belt_damp, belt_kv, belt_invw;
   int belt_geom, belt_class;
