@@ -1339,11 +1339,15 @@ FM_PH void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
     for (int ci = c0; ci < c1; ++ci) maxd = fmaxf(maxd, c_res(s, s.isl_list[ci]));
     FM_DBG(fm_dbg_islands++;)
     FM_DBG(int dbg_kind = has_arm ? (c1 > c0 ? 2 : 1) : 0; fm_dbg_cnt[4 + 4 * dbg_kind]++; fm_dbg_cnt[7 + 4 * dbg_kind] += c1 - c0;)
-    if (maxd < tol) continue;
+    // a lone cube is solved exactly by the lane's Newton at no extra cost to the block (lock step: some lane runs it in nearly every
+    // sub-step anyway), so its warm start only counts as converged far below the sweeps' stopping criterion: resting cubes then keep
+    // |v| < 1e-7 m/s instead of drifting inside the tolerance band
+    const bool newton_ok = !has_arm && node < FM_NCUBE && c1 - c0 <= 8;
+    if (maxd < (newton_ok ? 0.02f * tol : tol)) continue;
     bool alone = true;                                       // no other node was merged into this island
     if (s.need_union & 1) for (int i = 0; i < NN; ++i) alone = alone && (i == node || s.isl_root[i] != node);
     bool solved = false;
-    if (!has_arm && node < FM_NCUBE && c1 - c0 <= 8 && alone) {
+    if (newton_ok && alone) {
 #ifndef FM_NO_NEWTON
       solved = island_newton_cube(s, m, node, c0, c1, tol);
 #endif
