@@ -152,7 +152,7 @@ def test_auto_reset_and_episode_info():
 
 def test_mean_collected_objects_within_oracle_ci():
     """BASELINE.json: mean collected objects under a fixed policy must fall within the reference's 95% confidence interval.
-    Fixed policy = IK base policy, 2 arms; interval from 96 oracle episodes (tests/golden/ik_policy_stats.json, made by
+    Fixed policy = IK base policy, 2 arms; interval from 128 oracle episodes (tests/golden/ik_policy_stats.json, made by
     tools/make_policy_stats.py — the reference itself cannot run here); GPU: 1024 envs, same horizon and bookkeeping."""
     import json, os
     from factory_marl_b200.vec_env import FactoryVecEnv
