@@ -1323,6 +1323,8 @@ FM_HD void island_pgs_sweeps(EnvS<NA>& s, const FmDevModel& m, int node, int c0,
 // contacts (grasps, crashes, cube on cube) are only MARKED here (bit 8 + node of need_union) and solved in the next interval by a
 // whole warp each (ph_big_islands).  What is left (a lone arm's limit rows) is swept here.
 #define FM_BIG_BIT(node) (1 << (8 + (node)))
+#define FM_BIG_LARGE (1 << 24)   // some marked island of the env has more than FM_SLOT_NU unknowns: it needs the env's whole scratch
+#define FM_SLOT_NU 15            // an arm and at most one cube
 template <int NA, int E, bool BIGN>
 FM_PH void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
@@ -1355,7 +1357,12 @@ FM_PH void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
     }
     if (solved) continue;
     // a warp takes the stiff islands (an arm with contacts: 32 sweeps would not converge them); cube-on-cube islands converge in a few sweeps
-    if (BIGN && has_arm && c1 > c0) { FM_ATOMIC_OR(&s.need_union, FM_BIG_BIT(node)); continue; }
+    if (BIGN && has_arm && c1 > c0) {
+      int nu = 0;
+      for (int i = 0; i < NN; ++i) if (s.isl_root[i] == node) nu += i >= FM_NCUBE ? 9 : 6;
+      FM_ATOMIC_OR(&s.need_union, FM_BIG_BIT(node) | (nu > FM_SLOT_NU ? FM_BIG_LARGE : 0));
+      continue;
+    }
     island_pgs_sweeps(s, m, node, c0, c1, has_arm, single_row, inner, tol);
   }
 }
@@ -1371,7 +1378,7 @@ FM_PH void ph_pgs(EnvS<NA>* S, const FmDevModel& m, int tid, int T, int inner, f
 // crosses a stage lives in shared memory that is dead at this point of the sub-step (the Newton-Euler scratch d_f, d_n, d_comp and
 // the raw-contact keys), so the same source runs in the host-compiled test build with a loop over the 32 lanes per stage.
 #define FM_BIG_NU 24
-#define FM_BIG_NC 24
+#define FM_BIG_AW 8    // words of the active-set bit sets: 4 rows per contact + the arm rows <= 256
 // generalised force of arm dof d without constraints: actuator - bias (same expressions as ph_smooth)
 template <int NA>
 FM_HD float arm_qfrc(const EnvS<NA>& s, const FmDevModel& m, int a, int d) {
@@ -1451,8 +1458,10 @@ struct BigIsl {
   }
 };
 
+// slot < 0: the island has the env's whole scratch; slot >= 0: the env's marked islands (all <= FM_SLOT_NU unknowns) run on different
+// warps at the same time, each in its own part of the scratch
 template <int NA, class Lanes>
-FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes& L, float tol) {
+FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes& L, float tol, int slot) {
   const int NN = EnvS<NA>::NNODE;
   BigIsl<NA> B(s, m);
   B.nnode = 0; B.NU = 0; B.nrow_arm = 0;
@@ -1466,105 +1475,112 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
   B.off[B.nnode] = B.NU;
   B.c0 = s.isl_start[root]; B.nc = s.isl_start[root + 1] - B.c0;
   const int NU = B.NU, nc = B.nc, nrows = 4 * nc + B.nrow_arm;
-  if (NU > FM_BIG_NU || nc > FM_BIG_NC || nc + B.nrow_arm > 32 || nrows > 128) return false;
+  FM_DBG(if (NU > FM_BIG_NU) fm_dbg_sat[335]++; else if (nrows > 32 * FM_BIG_AW) fm_dbg_sat[336]++;)
+  if (NU > (slot < 0 ? FM_BIG_NU : FM_SLOT_NU) || nrows > 32 * FM_BIG_AW) return false;
   // scratch.  H: packed lower triangle of the (NU + 1) x (NU + 1) matrix [H g; g^T .] — lane i owns row i, the right-hand side is
   // row NU, so the forward substitution falls out of the factorisation; a: NU accelerations (Jacobi scale factors meanwhile).
-  // Both sit in the dead Newton-Euler buffers (d_f, d_n, d_comp: 352 floats); the contact staging and the bit sets in the raw keys.
-  B.H = &s.d_f[0][0][0]; B.g = B.H + tri(NU, 0); B.a = B.H + 326;
+  // Both sit in the dead Newton-Euler buffers (d_f, d_n, d_comp: 176 floats per arm); the contact staging (JS floats per Jacobian
+  // row) and the bit sets in the raw-contact keys and in the previous solve's keys (dead between the warm-start look-up of
+  // ph_contact_setup and ph_save_forces).
+  const int JS = slot < 0 ? FM_BIG_NU : FM_SLOT_NU + 1;
   float* rb = reinterpret_cast<float*>(&s.raw_key[0]);
-  B.Jc = rb; B.Wg = rb + 72; B.act = reinterpret_cast<unsigned*>(rb + 81); B.prev = B.act + 4; B.chg = reinterpret_cast<int*>(B.prev + 4);
+  float* small;                                               // Wg (9), act, prev (FM_BIG_AW each), chg
+  const int NSMALL = 10 + 2 * FM_BIG_AW;
+  if (slot < 0) { B.H = &s.d_f[0][0][0]; B.a = B.H + 326; B.Jc = rb; small = rb + 3 * FM_BIG_NU; }
+  else {
+    B.H = &s.d_f[0][0][0] + 176 * slot; B.a = B.H + 152;
+    const int per = 3 * (FM_SLOT_NU + 1) + NSMALL, whole = (2 * FmCap<NA>::CON) / per;   // slots that fit the raw keys entirely
+    if (slot < whole) { B.Jc = rb + per * slot; small = B.Jc + 3 * (FM_SLOT_NU + 1); }
+    else { B.Jc = reinterpret_cast<float*>(&s.prev_key[0]) + 3 * (FM_SLOT_NU + 1) * (slot - whole); small = rb + per * whole + NSMALL * (slot - whole); }
+  }
+  B.g = B.H + tri(NU, 0);
+  B.Wg = small; B.act = reinterpret_cast<unsigned*>(small + 9); B.prev = B.act + FM_BIG_AW; B.chg = reinterpret_cast<int*>(B.prev + FM_BIG_AW);
+  const int nitem = nc + B.nrow_arm;                          // active-set work items: a contact (4 rows) or an arm row
   L.stage([&](int lane) {
     if (lane < NU) { int ni, q; B.unk(lane, ni, q); B.a[lane] = s.acc[B.acc_index(ni, q)]; }
-    if (lane < 4) { B.act[lane] = 0u; B.prev[lane] = 0xFFFFFFFFu; }
+    if (lane < FM_BIG_AW) { B.act[lane] = 0u; B.prev[lane] = 0xFFFFFFFFu; }
     if (lane == 0) *B.chg = 0;
   });
   bool ok = false;
   for (int it = 0; it < 7; ++it) {
     FM_DBG(fm_dbg_sat[331]++;)
-    // ---- active set at the current a: one lane per contact (4 rows) or per arm row
+    // ---- active set at the current a: one work item per contact (4 rows) or per arm row
     L.stage([&](int lane) {
-      if (lane < nc) {
-        const int c = s.isl_list[B.c0 + lane];
-        float u[3]; B.contact_u(c, B.a, u);
-        const float mu = s.c_mu[c];
-        unsigned bits = 0; float mx = 0.f;
-        for (int r = 0; r < 4; ++r) {
-          const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
-          const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
-          const bool on = x < 0.f;
-          const int bit = 4 * lane + r;
-          if (on) bits |= 1u << (bit & 31);
-          if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) mx = fmaxf(mx, fabsf(x));
+      for (int item = lane; item < nitem; item += 32) {
+        if (item < nc) {
+          const int c = s.isl_list[B.c0 + item];
+          float u[3]; B.contact_u(c, B.a, u);
+          const float mu = s.c_mu[c];
+          unsigned bits = 0; float mx = 0.f;
+          for (int r = 0; r < 4; ++r) {
+            const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+            const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
+            const bool on = x < 0.f;
+            const int bit = 4 * item + r;
+            if (on) bits |= 1u << (bit & 31);
+            if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) mx = fmaxf(mx, fabsf(x));
+          }
+          if (bits) FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[(4 * item) >> 5]), (int)bits);
+          if (mx > 0.f) { int mi; memcpy(&mi, &mx, 4); FM_ATOMIC_MAXI(B.chg, mi); }
+        } else {
+          int rr = item - nc, ni = 0;
+          while (!(B.nodes[ni] >= FM_NCUBE && rr >= B.arm_row0[ni] && rr < B.arm_row0[ni] + s.arow_n[B.nodes[ni] - FM_NCUBE])) ++ni;
+          const int a = B.nodes[ni] - FM_NCUBE, r = rr - B.arm_row0[ni];
+          const int code = s.arow_code[a][r];
+          const float* aa = B.a + B.off[ni];
+          float x; bool on;
+          if (code & 0x1000) { x = aa[7] - aa[8] - s.arow_aref[a][r]; on = true; }
+          else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; x = sg * aa[d] - s.arow_aref[a][r]; on = x < 0.f; }
+          const int bit = 4 * nc + rr;
+          if (on) FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[bit >> 5]), (int)(1u << (bit & 31)));
+          if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) { float ax = fabsf(x); int mi; memcpy(&mi, &ax, 4); FM_ATOMIC_MAXI(B.chg, mi); }
         }
-        FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[(4 * lane) >> 5]), (int)bits);
-        int mi; memcpy(&mi, &mx, 4); FM_ATOMIC_MAXI(B.chg, mi);
-      } else if (lane < nc + B.nrow_arm) {
-        int rr = lane - nc, ni = 0;
-        while (!(B.nodes[ni] >= FM_NCUBE && rr >= B.arm_row0[ni] && rr < B.arm_row0[ni] + s.arow_n[B.nodes[ni] - FM_NCUBE])) ++ni;
-        const int a = B.nodes[ni] - FM_NCUBE, r = rr - B.arm_row0[ni];
-        const int code = s.arow_code[a][r];
-        const float* aa = B.a + B.off[ni];
-        float x; bool on;
-        if (code & 0x1000) { x = aa[7] - aa[8] - s.arow_aref[a][r]; on = true; }
-        else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; x = sg * aa[d] - s.arow_aref[a][r]; on = x < 0.f; }
-        const int bit = 4 * nc + rr;
-        if (on) FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[bit >> 5]), (int)(1u << (bit & 31)));
-        if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) { float ax = fabsf(x); int mi; memcpy(&mi, &ax, 4); FM_ATOMIC_MAXI(B.chg, mi); }
       }
     });
     {
       bool same = true;
-      for (int w = 0; w < 4; ++w) same = same && B.act[w] == B.prev[w];
+      for (int w = 0; w < FM_BIG_AW; ++w) same = same && B.act[w] == B.prev[w];
       float cg; memcpy(&cg, B.chg, 4);
       L.sync();                                               // every lane has read act / prev / chg before the next stage rewrites them
       if (it > 0 && (same || cg < tol)) { ok = true; break; }
       if (it == 6) break;
     }
     // ---- rows of [H g]: the nodes' inertia blocks, M a0, and the arm-local rows (one or two non-zeros each); lane i owns row i
+    // of H and entry i of the right-hand side row g_i = (M a0)_i (+ the active arm rows' J^T aref / R)
     L.stage([&](int lane) {
-      if (lane < 4) B.prev[lane] = B.act[lane];
+      if (lane < FM_BIG_AW) B.prev[lane] = B.act[lane];
       if (lane == 0) *B.chg = 0;
       if (lane > NU) return;
+      if (lane == NU) { B.g[NU] = 0.f; return; }
       float* row = B.H + tri(lane, 0);
-      if (lane == NU) {                                      // the right-hand side row: g_j = (M a0)_j (+ the active arm rows' J^T aref / R)
-        for (int j = 0; j < NU; ++j) {
-          int nj, qj; B.unk(j, nj, qj);
-          const int nd = B.nodes[nj];
-          row[j] = nd < FM_NCUBE ? (qj == 2 ? -m.g / m.cube_invm[nd] : 0.f) : arm_qfrc(s, m, nd - FM_NCUBE, qj);
-        }
-        row[NU] = 0.f;
-      } else {
-        int ni, qi; B.unk(lane, ni, qi);
-        const int nd = B.nodes[ni], o = B.off[ni];
-        for (int j = 0; j <= lane; ++j) {
-          float v = 0.f;
-          if (j >= o) v = nd < FM_NCUBE ? (j == lane ? (qi < 3 ? 1.f / m.cube_invm[nd] : 1.f / m.cube_invI[nd]) : 0.f) : s.M[nd - FM_NCUBE][tri(qi, j - o)];
-          row[j] = v;
-        }
+      int ni, qi; B.unk(lane, ni, qi);
+      const int nd = B.nodes[ni], o = B.off[ni];
+      for (int j = 0; j <= lane; ++j) {
+        float v = 0.f;
+        if (j >= o) v = nd < FM_NCUBE ? (j == lane ? (qi < 3 ? 1.f / m.cube_invm[nd] : 1.f / m.cube_invI[nd]) : 0.f) : s.M[nd - FM_NCUBE][tri(qi, j - o)];
+        row[j] = v;
       }
-      for (int ni = 0; ni < B.nnode; ++ni) {               // arm rows touching this lane's row
-        if (B.nodes[ni] < FM_NCUBE) continue;
-        const int a = B.nodes[ni] - FM_NCUBE, o = B.off[ni];
+      float gi = nd < FM_NCUBE ? (qi == 2 ? -m.g / m.cube_invm[nd] : 0.f) : arm_qfrc(s, m, nd - FM_NCUBE, qi);
+      if (nd >= FM_NCUBE) {                                  // arm rows touching this dof
+        const int a = nd - FM_NCUBE;
         for (int r = 0; r < s.arow_n[a]; ++r) {
           const int bit = 4 * nc + B.arm_row0[ni] + r;
           if (!((B.act[bit >> 5] >> (bit & 31)) & 1u)) continue;
           const int code = s.arow_code[a][r]; const float D = 1.f / s.arow_R[a][r], ar = s.arow_aref[a][r];
           if (code & 0x1000) {
-            const int i7 = o + 7, i8 = o + 8;
-            if (lane == i7) row[i7] += D; else if (lane == i8) { row[i8] += D; row[i7] -= D; }
-            else if (lane == NU) { row[i7] += D * ar; row[i8] -= D * ar; }
-          } else {
-            const int d = o + (code & 255); const float sg = (code >> 8) ? -1.f : 1.f;
-            if (lane == d) row[d] += D; else if (lane == NU) row[d] += sg * D * ar;
-          }
+            if (qi == 7) { row[lane] += D; gi += D * ar; }
+            else if (qi == 8) { row[lane] += D; row[lane - 1] -= D; gi -= D * ar; }
+          } else if ((code & 255) == qi) { row[lane] += D; gi += ((code >> 8) ? -1.f : 1.f) * D * ar; }
         }
       }
+      B.g[lane] = gi;
     });
     // ---- contacts: H += J_c^T W_c J_c, g += J_c^T g_c, one contact after the other (columns staged by the lanes, W_c by lane 31)
     for (int ci = 0; ci < nc; ++ci) {
       const int c = s.isl_list[B.c0 + ci];
+      FM_DBG(fm_dbg_sat[338]++; if ((B.act[(4 * ci) >> 5] >> ((4 * ci) & 31)) & 15u) fm_dbg_sat[339]++;)
       L.stage([&](int lane) {
-        if (lane < NU) { float jc[3]; B.jcol(c, lane, jc); B.Jc[lane] = jc[0]; B.Jc[24 + lane] = jc[1]; B.Jc[48 + lane] = jc[2]; }
+        if (lane < NU) { float jc[3]; B.jcol(c, lane, jc); B.Jc[lane] = jc[0]; B.Jc[JS + lane] = jc[1]; B.Jc[2 * JS + lane] = jc[2]; }
         if (lane == 31) {      // 3x3 weight of the contact's active pyramid rows and the matching right-hand side
           float W[6] = {0, 0, 0, 0, 0, 0}, gc[3] = {0, 0, 0}, kb[3];
           B.belt_const(c, kb);
@@ -1586,14 +1602,14 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
         float t0, t1, t2;
         if (lane == NU) { t0 = B.Wg[6]; t1 = B.Wg[7]; t2 = B.Wg[8]; }           // g row: J_c^T g_c
         else {
-          const float i0 = B.Jc[lane], i1 = B.Jc[24 + lane], i2 = B.Jc[48 + lane];
+          const float i0 = B.Jc[lane], i1 = B.Jc[JS + lane], i2 = B.Jc[2 * JS + lane];
           if (i0 == 0.f && i1 == 0.f && i2 == 0.f) return;
           const float W00 = B.Wg[0], W11 = B.Wg[1], W22 = B.Wg[2], W01 = B.Wg[3], W02 = B.Wg[4];   // the pyramid has no (t1, t2) term
           t0 = W00 * i0 + W01 * i1 + W02 * i2; t1 = W01 * i0 + W11 * i1; t2 = W02 * i0 + W22 * i2;
         }
         float* row = B.H + tri(lane, 0);
         const int jn = lane == NU ? NU : lane + 1;
-        for (int j = 0; j < jn; ++j) row[j] += t0 * B.Jc[j] + t1 * B.Jc[24 + j] + t2 * B.Jc[48 + j];
+        for (int j = 0; j < jn; ++j) row[j] += t0 * B.Jc[j] + t1 * B.Jc[JS + j] + t2 * B.Jc[2 * JS + j];
       });
     }
     // ---- Jacobi scaling (the arm's inertias span three decades): S = diag(H)^-1/2, [H g] <- S [H g] S
@@ -1607,7 +1623,7 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
     });
     // ---- left-looking Cholesky, one stage per column, lane i = row i (row NU carries the right-hand side: y = L^-1 g).  The
     // factor's diagonal goes to dg (the contact staging is dead now): the unfactored H[k][k] must stay readable in this stage
-    float* dg = B.Jc; float* xs = B.Jc + 24;
+    float* dg = B.Jc; float* xs = B.Jc + JS;
     for (int k = 0; k < NU; ++k) {
       L.stage([&](int lane) {
         if (lane < k || lane > NU) return;
@@ -1626,70 +1642,90 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
         if (lane == k) xs[k] = xk; else B.g[lane] -= B.H[tri(k, lane)] * xk;
       });
     }
-    L.stage([&](int lane) { if (lane < NU) B.a[lane] *= xs[lane]; if (lane < 4) B.act[lane] = 0u; });
+    L.stage([&](int lane) { if (lane < NU) B.a[lane] *= xs[lane]; if (lane < FM_BIG_AW) B.act[lane] = 0u; });
   }
   FM_DBG(fm_dbg_sat[332] += ok; fm_dbg_sat[340 + (nc < 24 ? nc : 24)]++; fm_dbg_sat[370 + NU]++;)
   if (!ok) return false;
   // ---- accept: accelerations, forces f = max(-x, 0) / R of the final a, belt projections
   L.stage([&](int lane) {
     if (lane < NU) { int ni, q; B.unk(lane, ni, q); s.acc[B.acc_index(ni, q)] = B.a[lane]; }
-    if (lane < nc) {
-      const int c = s.isl_list[B.c0 + lane];
-      float u[3]; B.contact_u(c, B.a, u);
-      const float mu = s.c_mu[c], D = 1.f / s.c_R[c];
-      float f[4];
-      for (int r = 0; r < 4; ++r) {
-        const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
-        const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
-        f[r] = x < 0.f ? -D * x : 0.f;
-        s.c_f[c][r] = f[r];
+    for (int item = lane; item < nitem; item += 32) {
+      if (item < nc) {
+        const int c = s.isl_list[B.c0 + item];
+        float u[3]; B.contact_u(c, B.a, u);
+        const float mu = s.c_mu[c], D = 1.f / s.c_R[c];
+        float f[4];
+        for (int r = 0; r < 4; ++r) {
+          const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+          const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
+          f[r] = x < 0.f ? -D * x : 0.f;
+          s.c_f[c][r] = f[r];
+        }
+        float bs = 0.f;
+        const int cs = s.c_side[c];
+        for (int sd_i = 0; sd_i < 2; ++sd_i) {
+          const int sd = (cs >> (FM_SIDE_BITS * sd_i)) & FM_SIDE_MASK;
+          if (side_type(sd) != FM_SIDE_BELT) continue;
+          const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
+          const float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
+          bs += (sd_i ? 1.f : -1.f) * (n.y * Fn + t1.y * F1 + t2.y * F2);
+        }
+        c_belt(s, c) = bs;
+      } else {
+        int rr = item - nc, ni = 0;
+        while (!(B.nodes[ni] >= FM_NCUBE && rr >= B.arm_row0[ni] && rr < B.arm_row0[ni] + s.arow_n[B.nodes[ni] - FM_NCUBE])) ++ni;
+        const int a = B.nodes[ni] - FM_NCUBE, r = rr - B.arm_row0[ni];
+        const int code = s.arow_code[a][r];
+        const float* aa = B.a + B.off[ni];
+        const float D = 1.f / s.arow_R[a][r];
+        if (code & 0x1000) s.arow_f[a][r] = -D * (aa[7] - aa[8] - s.arow_aref[a][r]);
+        else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; const float x = sg * aa[d] - s.arow_aref[a][r]; s.arow_f[a][r] = x < 0.f ? -D * x : 0.f; }
       }
-      float bs = 0.f;
-      const int cs = s.c_side[c];
-      for (int sd_i = 0; sd_i < 2; ++sd_i) {
-        const int sd = (cs >> (FM_SIDE_BITS * sd_i)) & FM_SIDE_MASK;
-        if (side_type(sd) != FM_SIDE_BELT) continue;
-        const f3 n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); const f3 t2 = cross3(n, t1);
-        const float Fn = f[0] + f[1] + f[2] + f[3], F1 = mu * (f[0] - f[1]), F2 = mu * (f[2] - f[3]);
-        bs += (sd_i ? 1.f : -1.f) * (n.y * Fn + t1.y * F1 + t2.y * F2);
-      }
-      c_belt(s, c) = bs;
-    } else if (lane < nc + B.nrow_arm) {
-      int rr = lane - nc, ni = 0;
-      while (!(B.nodes[ni] >= FM_NCUBE && rr >= B.arm_row0[ni] && rr < B.arm_row0[ni] + s.arow_n[B.nodes[ni] - FM_NCUBE])) ++ni;
-      const int a = B.nodes[ni] - FM_NCUBE, r = rr - B.arm_row0[ni];
-      const int code = s.arow_code[a][r];
-      const float* aa = B.a + B.off[ni];
-      const float D = 1.f / s.arow_R[a][r];
-      if (code & 0x1000) s.arow_f[a][r] = -D * (aa[7] - aa[8] - s.arow_aref[a][r]);
-      else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; const float x = sg * aa[d] - s.arow_aref[a][r]; s.arow_f[a][r] = x < 0.f ? -D * x : 0.f; }
     }
   });
   return true;
 }
 
 // phase: one warp per marked island (see ph_pgs); an island the Newton cannot take or settle falls back to the sweeps on one lane
+FM_HD int popc_u(unsigned v) { int n = 0; for (; v; v &= v - 1) ++n; return n; }
 template <int NA, int E, class Lanes>
 FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps, Lanes& L, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int NN = EnvS<NA>::NNODE;
-  // all marked islands of one env go to the SAME warp, one after the other: they share the env's scratch (H, g, a, staging)
-  for (int w = warp; w < E; w += nwarps) for (int node = 0; node < NN; ++node) {
-    EnvS<NA>& s = S[w];
-    if (!(s.need_union & FM_BIG_BIT(node))) continue;
-    FM_DBG(fm_dbg_sat[330]++;)
-    const bool ok = island_newton_warp<NA>(s, m, node, L, tol);
-    if (!ok) {
-      FM_DBG(fm_dbg_sat[333]++; long long sw0 = fm_dbg_sweeps;)
-      L.stage([&](int lane) {
-        if (lane != 0) return;
-        const int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
-        bool has_arm = false;
-        for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
-        island_pgs_sweeps(s, m, node, c0, c1, has_arm, false, inner, tol);
-      });
-      FM_DBG(fm_dbg_sat[334] += fm_dbg_sweeps - sw0;)
+  const int NSLOT = NA == 2 ? 2 : 3;     // islands of one env that can be solved side by side (scratch partition, island_newton_warp)
+  // work items in a fixed order, item i -> warp i % nwarps.  The marked islands of an env are separate items (different warps, own
+  // scratch slot each) when they all are small and few enough; otherwise the env is ONE item and its islands run one after the other.
+  int item = 0;
+  for (int e = 0; e < E; ++e) {
+    EnvS<NA>& s = S[e];
+    const int nu = s.need_union;
+    const unsigned big = ((unsigned)nu >> 8) & ((1u << NN) - 1u);
+    if (!big) continue;
+    const int nb = popc_u(big);
+    const bool split = nb > 1 && nb <= NSLOT && !(nu & FM_BIG_LARGE);
+    int slot = 0;
+    for (int node = 0; node < NN; ++node) {
+      if (!((big >> node) & 1u)) continue;
+      const bool mine = (item % nwarps) == warp;
+      if (split) { ++item; }
+      if (mine) {
+        FM_DBG(fm_dbg_sat[330]++;)
+        const bool ok = island_newton_warp<NA>(s, m, node, L, tol, split ? slot : -1);
+        if (!ok) {
+          FM_DBG(fm_dbg_sat[333]++; long long sw0 = fm_dbg_sweeps;)
+          L.stage([&](int lane) {
+            if (lane != 0) return;
+            const int c0 = s.isl_start[node], c1 = s.isl_start[node + 1];
+            bool has_arm = false;
+            for (int a = 0; a < NA; ++a) has_arm = has_arm || s.isl_root[FM_NCUBE + a] == node;
+            island_pgs_sweeps(s, m, node, c0, c1, has_arm, false, inner, tol);
+          });
+          FM_DBG(fm_dbg_sat[334] += fm_dbg_sweeps - sw0;)
+        }
+      }
+      ++slot;
     }
+    if (!split) ++item;
   }
 }
 
