@@ -39,6 +39,8 @@ struct DevLanes {
   int lane;
   template <class G> __device__ __forceinline__ void stage(G g) { g(lane); __syncwarp(); }
   __device__ __forceinline__ void sync() { __syncwarp(); }
+  template <class G> __device__ __forceinline__ void run(G g) { g(lane); }   // no synchronisation after it
+  template <class T, int N> struct Arr { T a[N]; __device__ __forceinline__ T* operator()(int) { return a; } };   // per-lane registers
 };
 struct DevRun {
   template <class F> __device__ __forceinline__ void operator()(F f) { f((int)threadIdx.x); __syncthreads(); }

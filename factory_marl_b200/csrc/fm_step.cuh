@@ -1090,8 +1090,10 @@ FM_PH void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 // contact-space acceleration u = J a (3x3 Delassus block W).  commit = false only evaluates (convergence check from the
 // warm start); commit = true stores the forces and applies Minv J^T dlam.  The belt-dof projection of the contact's force is
 // left in c_belt(c) either way (lagged belt coupling, summed by ph_belt).  Returns max |df| * A_rr.
-template <int NA> FM_HD float& c_res(EnvS<NA>& s, int c) { return s.raw_d[c][0]; }    // raw contact buffer is dead after ph_contact_setup
-template <int NA> FM_HD float& c_belt(EnvS<NA>& s, int c) { return s.raw_d[c][1]; }
+// the raw contact buffer is dead after ph_contact_setup: its key words hold the per-contact residual and belt projection from
+// ph_check on, its data words (raw_d) are the scratch of the big-island solve
+template <int NA> FM_HD float& c_res(EnvS<NA>& s, int c) { return reinterpret_cast<float*>(&s.raw_key[0])[c]; }
+template <int NA> FM_HD float& c_belt(EnvS<NA>& s, int c) { return reinterpret_cast<float*>(&s.raw_g[0])[c]; }
 template <int NA>
 FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool commit) {
   int cs = s.c_side[c];
@@ -1392,6 +1394,11 @@ FM_HD float arm_qfrc(const EnvS<NA>& s, const FmDevModel& m, int a, int d) {
   return (d == 7 ? m.ten0 : m.ten1) * f - s.bias[a][d];
 }
 
+// islands of one env that can be solved side by side, and the raw-contact data words each of them gets as staging
+template <int NA> struct BigSlots {
+  static const int N = NA == 2 ? 2 : 3, SL = FmCap<NA>::CON * 7 / N;
+  static_assert(SL >= 12 * (FM_SLOT_NU + 1) && (2 * FM_BIG_AW + 1) * N <= FmCap<NA>::CON, "slot staging does not fit");
+};
 template <int NA>
 struct BigIsl {
   EnvS<NA>& s; const FmDevModel& m;
@@ -1464,6 +1471,7 @@ template <int NA, class Lanes>
 FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes& L, float tol, int slot) {
   const int NN = EnvS<NA>::NNODE;
   BigIsl<NA> B(s, m);
+  typename Lanes::template Arr<int, 5> eij; typename Lanes::template Arr<float, 5> acc;   // per-lane registers that cross stages
   B.nnode = 0; B.NU = 0; B.nrow_arm = 0;
   for (int i = 0; i < NN; ++i)
     if (s.isl_root[i] == root) {
@@ -1480,21 +1488,19 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
   // scratch.  H: packed lower triangle of the (NU + 1) x (NU + 1) matrix [H g; g^T .] — lane i owns row i, the right-hand side is
   // row NU, so the forward substitution falls out of the factorisation; a: NU accelerations (Jacobi scale factors meanwhile).
   // Both sit in the dead Newton-Euler buffers (d_f, d_n, d_comp: 176 floats per arm); the contact staging (JS floats per Jacobian
-  // row) and the bit sets in the raw-contact keys and in the previous solve's keys (dead between the warm-start look-up of
-  // ph_contact_setup and ph_save_forces).
+  // row) in the dead raw-contact data, the bit sets behind it or (slots) in the previous solve's keys, which are dead between the
+  // warm-start look-up of ph_contact_setup and ph_save_forces.
   const int JS = slot < 0 ? FM_BIG_NU : FM_SLOT_NU + 1;
-  float* rb = reinterpret_cast<float*>(&s.raw_key[0]);
-  float* small;                                               // Wg (9), act, prev (FM_BIG_AW each), chg
-  const int NSMALL = 10 + 2 * FM_BIG_AW;
-  if (slot < 0) { B.H = &s.d_f[0][0][0]; B.a = B.H + 326; B.Jc = rb; small = rb + 3 * FM_BIG_NU; }
+  float* rd = &s.raw_d[0][0];
+  float* small;                                               // act, prev (FM_BIG_AW words each), chg
+  if (slot < 0) { B.H = &s.d_f[0][0][0]; B.a = B.H + 326; B.Jc = rd; B.Wg = rd + 3 * FM_BIG_NU; small = B.Wg + 9; }
   else {
     B.H = &s.d_f[0][0][0] + 176 * slot; B.a = B.H + 152;
-    const int per = 3 * (FM_SLOT_NU + 1) + NSMALL, whole = (2 * FmCap<NA>::CON) / per;   // slots that fit the raw keys entirely
-    if (slot < whole) { B.Jc = rb + per * slot; small = B.Jc + 3 * (FM_SLOT_NU + 1); }
-    else { B.Jc = reinterpret_cast<float*>(&s.prev_key[0]) + 3 * (FM_SLOT_NU + 1) * (slot - whole); small = rb + per * whole + NSMALL * (slot - whole); }
+    B.Jc = rd + BigSlots<NA>::SL * slot; B.Wg = nullptr;      // two buffers of (J, W J) columns, 6 x JS each
+    small = reinterpret_cast<float*>(&s.prev_key[0]) + (2 * FM_BIG_AW + 1) * slot;
   }
   B.g = B.H + tri(NU, 0);
-  B.Wg = small; B.act = reinterpret_cast<unsigned*>(small + 9); B.prev = B.act + FM_BIG_AW; B.chg = reinterpret_cast<int*>(B.prev + FM_BIG_AW);
+  B.act = reinterpret_cast<unsigned*>(small); B.prev = B.act + FM_BIG_AW; B.chg = reinterpret_cast<int*>(B.prev + FM_BIG_AW);
   const int nitem = nc + B.nrow_arm;                          // active-set work items: a contact (4 rows) or an arm row
   L.stage([&](int lane) {
     if (lane < NU) { int ni, q; B.unk(lane, ni, q); B.a[lane] = s.acc[B.acc_index(ni, q)]; }
@@ -1575,7 +1581,61 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
       }
       B.g[lane] = gi;
     });
-    // ---- contacts: H += J_c^T W_c J_c, g += J_c^T g_c, one contact after the other (columns staged by the lanes, W_c by lane 31)
+    // ---- contacts: H += J_c^T W_c J_c, g += J_c^T g_c
+    if (slot >= 0) {
+      // (NU + 1) <= 16 rows: the packed triangle's <= 136 entries are dealt to the 32 lanes (entry e -> lane e % 32) and accumulated in
+      // registers over the contacts; per contact lane i < NU stages column i of J_c and of W_c J_c (lane NU: 0 and g_c) in one of two
+      // buffers, so one __syncwarp per contact suffices and the next contact's column work overlaps this one's accumulation
+      const int TE = tri(NU + 1, 0);
+      L.run([&](int lane) {
+        int* ij = eij(lane); float* ac = acc(lane);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int e = lane + 32 * k;
+          int i = NU, j = NU;
+          if (e < TE) { i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f); while (tri(i + 1, 0) <= e) ++i; while (tri(i, 0) > e) --i; j = e - tri(i, 0); }
+          ij[k] = (i << 8) | j; ac[k] = 0.f;
+        }
+      });
+      for (int ci = 0; ci < nc; ++ci) {
+        const int c = s.isl_list[B.c0 + ci];
+        float* bj = B.Jc + 6 * JS * (ci & 1);
+        L.stage([&](int lane) {
+          if (lane > NU) return;
+          float W00 = 0.f, W11 = 0.f, W22 = 0.f, W01 = 0.f, W02 = 0.f, gc[3] = {0, 0, 0}, kb[3];   // the pyramid has no (t1, t2) term
+          B.belt_const(c, kb);
+          const float mu = s.c_mu[c], D = 1.f / s.c_R[c];
+          const unsigned bits = (B.act[(4 * ci) >> 5] >> ((4 * ci) & 31)) & 15u;
+          for (int r = 0; r < 4; ++r) {
+            if (!((bits >> r) & 1u)) continue;
+            const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
+            const float rhs = D * (s.c_aref[c][r] - kb[0] - cf * kb[tq]);
+            W00 += D; if (tq == 1) { W11 += D * cf * cf; W01 += D * cf; } else { W22 += D * cf * cf; W02 += D * cf; }
+            gc[0] += rhs; gc[tq] += cf * rhs;
+          }
+          float i0 = 0.f, i1 = 0.f, i2 = 0.f, t0 = gc[0], t1 = gc[1], t2 = gc[2];
+          if (lane < NU) {
+            float jc[3]; B.jcol(c, lane, jc); i0 = jc[0]; i1 = jc[1]; i2 = jc[2];
+            t0 = W00 * i0 + W01 * i1 + W02 * i2; t1 = W01 * i0 + W11 * i1; t2 = W02 * i0 + W22 * i2;
+          }
+          bj[lane] = i0; bj[JS + lane] = i1; bj[2 * JS + lane] = i2; bj[3 * JS + lane] = t0; bj[4 * JS + lane] = t1; bj[5 * JS + lane] = t2;
+        });
+        L.run([&](int lane) {
+          const int* ij = eij(lane); float* ac = acc(lane);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int i = ij[k] >> 8, j = ij[k] & 255;
+            ac[k] += bj[3 * JS + i] * bj[j] + bj[4 * JS + i] * bj[JS + j] + bj[5 * JS + i] * bj[2 * JS + j];
+          }
+        });
+      }
+      L.stage([&](int lane) {
+        const float* ac = acc(lane);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { const int e = lane + 32 * k; if (e < TE) B.H[e] += ac[k]; }
+      });
+    } else
+    // whole-scratch islands (rare): one contact after the other, columns staged by the lanes, W_c by lane 31, lane i updates row i
     for (int ci = 0; ci < nc; ++ci) {
       const int c = s.isl_list[B.c0 + ci];
       FM_DBG(fm_dbg_sat[338]++; if ((B.act[(4 * ci) >> 5] >> ((4 * ci) & 31)) & 15u) fm_dbg_sat[339]++;)
@@ -1692,7 +1752,7 @@ template <int NA, int E, class Lanes>
 FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps, Lanes& L, int inner, float tol) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m);
   const int NN = EnvS<NA>::NNODE;
-  const int NSLOT = NA == 2 ? 2 : 3;     // islands of one env that can be solved side by side (scratch partition, island_newton_warp)
+  const int NSLOT = BigSlots<NA>::N;
   // work items in a fixed order, item i -> warp i % nwarps.  The marked islands of an env are separate items (different warps, own
   // scratch slot each) when they all are small and few enough; otherwise the env is ONE item and its islands run one after the other.
   int item = 0;
@@ -1702,7 +1762,7 @@ FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps
     const unsigned big = ((unsigned)nu >> 8) & ((1u << NN) - 1u);
     if (!big) continue;
     const int nb = popc_u(big);
-    const bool split = nb > 1 && nb <= NSLOT && !(nu & FM_BIG_LARGE);
+    const bool slots = nb <= NSLOT && !(nu & FM_BIG_LARGE), split = slots && nb > 1;   // slots: every marked island is small
     int slot = 0;
     for (int node = 0; node < NN; ++node) {
       if (!((big >> node) & 1u)) continue;
@@ -1710,7 +1770,7 @@ FM_PH void ph_big_islands(EnvS<NA>* S, const FmDevModel& m, int warp, int nwarps
       if (split) { ++item; }
       if (mine) {
         FM_DBG(fm_dbg_sat[330]++;)
-        const bool ok = island_newton_warp<NA>(s, m, node, L, tol, split ? slot : -1);
+        const bool ok = island_newton_warp<NA>(s, m, node, L, tol, slots ? slot : -1);
         if (!ok) {
           FM_DBG(fm_dbg_sat[333]++; long long sw0 = fm_dbg_sweeps;)
           L.stage([&](int lane) {

@@ -23,6 +23,8 @@ struct HostLanes {
     else for (int k = 0; k < 32; ++k) g((k * 13 + 5) % 32);
   }
   void sync() {}
+  template <class G> void run(G g) { stage(g); }
+  template <class T, int N> struct Arr { T a[32][N]; T* operator()(int lane) { return a[lane]; } };
 };
 struct HostRun {
   int T;
