@@ -1587,6 +1587,7 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
       // registers over the contacts; per contact lane i < NU stages column i of J_c and of W_c J_c (lane NU: 0 and g_c) in one of two
       // buffers, so one __syncwarp per contact suffices and the next contact's column work overlaps this one's accumulation
       const int TE = tri(NU + 1, 0);
+      constexpr int JSS = FM_SLOT_NU + 1;
       L.run([&](int lane) {
         int* ij = eij(lane); float* ac = acc(lane);
 #pragma unroll
@@ -1599,7 +1600,7 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
       });
       for (int ci = 0; ci < nc; ++ci) {
         const int c = s.isl_list[B.c0 + ci];
-        float* bj = B.Jc + 6 * JS * (ci & 1);
+        float* bj = B.Jc + 6 * JSS * (ci & 1);
         L.stage([&](int lane) {
           if (lane > NU) return;
           float W00 = 0.f, W11 = 0.f, W22 = 0.f, W01 = 0.f, W02 = 0.f, gc[3] = {0, 0, 0}, kb[3];   // the pyramid has no (t1, t2) term
@@ -1624,8 +1625,8 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
           const int* ij = eij(lane); float* ac = acc(lane);
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
-            const int i = ij[k] >> 8, j = ij[k] & 255;
-            ac[k] += bj[3 * JS + i] * bj[j] + bj[4 * JS + i] * bj[JS + j] + bj[5 * JS + i] * bj[2 * JS + j];
+            const float* bi = bj + (ij[k] >> 8); const float* bq = bj + (ij[k] & 255);
+            ac[k] += bi[3 * JSS] * bq[0] + bi[4 * JSS] * bq[JSS] + bi[5 * JSS] * bq[2 * JSS];
           }
         });
       }
