@@ -32,8 +32,8 @@ class fm_state_view(C.Structure):
 class fm_debug_view(C.Structure):
     _fields_ = [("env", C.c_int32), ("ncon", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
                 ("pair", (C.c_int32 * 2) * 64), ("pos", (C.c_float * 3) * 64), ("normal", (C.c_float * 3) * 64),
-                ("force", (C.c_float * 4) * 64), ("site_xpos", (C.c_float * 3) * 4), ("mass_matrix", (C.c_float * 45) * 4),
-                ("bias", (C.c_float * 9) * 4), ("qacc_smooth", C.c_float * 97), ("qacc", C.c_float * 97)]
+                ("force", (C.c_float * 4) * 64), ("site_xpos", (C.c_float * 3) * 6), ("mass_matrix", (C.c_float * 45) * 6),
+                ("bias", (C.c_float * 9) * 6), ("qacc_smooth", C.c_float * 115), ("qacc", C.c_float * 115)]
 
 
 EXPORTS = ["fm_create", "fm_destroy", "fm_obs_dim", "fm_act_dim", "fm_state_rows", "fm_bind_state", "fm_field_offset",

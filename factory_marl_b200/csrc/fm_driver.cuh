@@ -124,7 +124,7 @@ FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
 
 // TW = warps per block (default: one warp per env of the block)
 template <int NA, int E, int TW = E, bool BIGN = false, class Run>
-FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class,
+FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const unsigned int* cpairs, const int* geom_class,
                          const FmEnvCfg& cfg, const FmStatePtrs& st, const FmStepArgs& ar, int env0) {
   const int T = 32 * TW;
   typedef Lay<NA> L;

@@ -38,7 +38,7 @@ inline void fm_build_host_model(const void* blob, size_t n, FmHostModel& H) {
   const int32_t* sizes = I(blob, n, "sizes");
   H.ngeom = sizes[1]; H.nq = sizes[3]; H.nv = sizes[4]; H.nu = sizes[5];
   m.n_arms = H.n_arms = I(blob, n, "n_arms")[0];
-  if (m.n_arms > FM_MAX_ARMS) throw std::runtime_error("num_arms > 4 is not supported by this build");
+  if (m.n_arms > FM_MAX_ARMS) throw std::runtime_error("num_arms > 6 is not supported by this build");
   if (I(blob, n, "n_cubes")[0] != FM_NCUBE) throw std::runtime_error("max_num_objects must be 10");
   const double* opt = D(blob, n, "opt");
   m.h = (float)opt[0]; m.g = (float)(-opt[1]); H.timestep = opt[0];

@@ -15,6 +15,10 @@
 #define FM_BIG4_E 7
 #define FM_BIG4_TW 7
 #endif
+#ifndef FM_BIG6_E
+#define FM_BIG6_E 6
+#define FM_BIG6_TW 8
+#endif
 #ifndef FM_MINBLK
 #define FM_MINBLK 1
 #endif
@@ -63,11 +67,11 @@ __global__ void __launch_bounds__(32 * TW, FM_MINBLK) fm_step_kernel(const FmDev
                                                              const int* __restrict__ geom_class, FmEnvCfg cfg, FmStatePtrs st, FmStepArgs ar) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvS<NA>* S = reinterpret_cast<EnvS<NA>*>(smem_raw);
-  TaskS* TS = reinterpret_cast<TaskS*>(S + E);
+  TaskS<NA>* TS = reinterpret_cast<TaskS<NA>*>(S + E);
   // zero the block's shared state (counters, lists)
   {
     int* z = reinterpret_cast<int*>(smem_raw);
-    const int nw = (int)((E * (sizeof(EnvS<NA>) + sizeof(TaskS))) / 4);
+    const int nw = (int)((E * (sizeof(EnvS<NA>) + sizeof(TaskS<NA>))) / 4);
     for (int i = threadIdx.x; i < nw; i += 32 * TW) z[i] = 0;
     __syncthreads();
   }
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(32 * TW, FM_MINBLK) fm_step_kernel(const FmDev
 
 template <int NA, int E, int TW, bool BIGN>
 cudaError_t fm_launch_step(const FmLaunch& L, const FmStepArgs& ar, cudaStream_t s) {
-  const size_t smem = E * (sizeof(EnvS<NA>) + sizeof(TaskS));
+  const size_t smem = E * (sizeof(EnvS<NA>) + sizeof(TaskS<NA>));
   {   // per device, not per process: set on every launch (cheap) so that a second GPU in the same process gets it too
     cudaError_t e = cudaFuncSetAttribute(fm_step_kernel<NA, E, TW, BIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -96,4 +100,7 @@ extern template cudaError_t fm_launch_step<4, 1, 1>(const FmLaunch&, const FmSte
 extern template cudaError_t fm_launch_step<4, 4, 4>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 extern template cudaError_t fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW, true>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<6, 1, 1>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
+extern template cudaError_t fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW, true>(const FmLaunch&, const FmStepArgs&, cudaStream_t);
 #endif

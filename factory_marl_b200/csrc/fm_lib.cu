@@ -40,6 +40,7 @@ static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   // IK-driven env classes (every class but AllFullRL) get the kernel variant with the warp-cooperative big-island solve
   const bool bign = h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1;     // fm_config.pgs_outer = 1: sweeps only
   if (h->hm.n_arms == 2) e = h->E == FM_BIG2_E ? (bign ? fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW, true>(L, ar, s) : fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW>(L, ar, s)) : (h->E == 1 ? fm_launch_step<2, 1, 1>(L, ar, s) : fm_launch_step<2, 4, 4>(L, ar, s));
+  else if (h->hm.n_arms == 6) e = h->E == 1 ? fm_launch_step<6, 1, 1>(L, ar, s) : (bign ? fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW, true>(L, ar, s) : fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW>(L, ar, s));
   else e = h->E == FM_BIG4_E ? (bign ? fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW, true>(L, ar, s) : fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(L, ar, s)) : (h->E == 1 ? fm_launch_step<4, 1, 1>(L, ar, s) : fm_launch_step<4, 4, 4>(L, ar, s));
   if (e != cudaSuccess) { g_err = std::string("fm_step_kernel launch: ") + cudaGetErrorString(e); return 2; }
   h->launches++;
@@ -56,13 +57,14 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     fm_handle* h = new fm_handle();
     fm_build_host_model(blob, n, h->hm);
     if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
-    if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4 are built");
+    if (h->hm.n_arms != 2 && h->hm.n_arms != 4 && h->hm.n_arms != 6) throw std::runtime_error("num_arms must be 2, 4 or 6 (scene.py:148-158)");
     if (cfg->env_class < 0 || cfg->env_class > 6) throw std::runtime_error("bad env_class");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
-    // envs per block: 1 | 4 | the one-block-per-SM shape (14 with two arms, 7 with four); 0 = by batch size
-    const int big = h->hm.n_arms == 2 ? FM_BIG2_E : FM_BIG4_E;
+    // envs per block: 1 | 4 | the one-block-per-SM shape (14 with two arms, 7 with four, 6 with six); 0 = by batch size
+    const int big = h->hm.n_arms == 2 ? FM_BIG2_E : (h->hm.n_arms == 4 ? FM_BIG4_E : FM_BIG6_E);
     int E = cfg->envs_per_block;
     h->E = (E == 1 || E == 4 || E == big) ? E : (cfg->n_envs >= 2048 ? big : 4);
+    if (h->hm.n_arms == 6 && h->E == 4) h->E = big;       // six arms: the one-env shape and the block of 6 only
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, nullptr};
     FM_CUDA(cudaMalloc(&h->d_model, sizeof(FmDevModel)));
     FM_CUDA(cudaMemcpy(h->d_model, &h->hm.dm, sizeof(FmDevModel), cudaMemcpyHostToDevice));
@@ -74,7 +76,7 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     FM_CUDA(cudaMemcpy(h->d_geom_class, h->hm.geom_class.data(), h->hm.geom_class.size() * sizeof(int), cudaMemcpyHostToDevice));
     FM_CUDA(cudaMalloc(&h->d_dump, sizeof(FmDebugDump)));
     const size_t ws_rows = (size_t)cfg->n_envs + 32;   // + padding slots of the last block
-    const size_t ws_floats = h->hm.n_arms == 2 ? FmCap<2>::WS : FmCap<4>::WS;
+    const size_t ws_floats = h->hm.n_arms == 2 ? FmCap<2>::WS : (h->hm.n_arms == 4 ? FmCap<4>::WS : FmCap<6>::WS);
     FM_CUDA(cudaMalloc(&h->d_ws, ws_rows * ws_floats * sizeof(float)));
     FM_CUDA(cudaMemset(h->d_ws, 0, ws_rows * ws_floats * sizeof(float)));
     h->st.ws = h->d_ws;
@@ -87,16 +89,16 @@ int fm_destroy(fm_handle* h) {
   cudaFree(h->d_model); cudaFree(h->d_ik); cudaFree(h->d_cpairs); cudaFree(h->d_geom_class); cudaFree(h->d_dump); cudaFree(h->d_ws);
   delete h; return 0;
 }
-int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : Lay<4>::obs_dim(h->cfg.env_class); }
+int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : (h->hm.n_arms == 4 ? Lay<4>::obs_dim(h->cfg.env_class) : Lay<6>::obs_dim(h->cfg.env_class)); }
 int fm_act_dim(const fm_handle* h) { return fm_act_dim_of(h->cfg.env_class, h->hm.n_arms); }
 int fm_state_rows(const fm_handle* h, int32_t* nf, int32_t* nd, int32_t* ni) {
-  if (h->hm.n_arms == 2) { *nf = Lay<2>::NF; *nd = Lay<2>::ND; *ni = Lay<2>::NI; } else { *nf = Lay<4>::NF; *nd = Lay<4>::ND; *ni = Lay<4>::NI; }
+  if (h->hm.n_arms == 2) { *nf = Lay<2>::NF; *nd = Lay<2>::ND; *ni = Lay<2>::NI; } else if (h->hm.n_arms == 4) { *nf = Lay<4>::NF; *nd = Lay<4>::ND; *ni = Lay<4>::NI; } else { *nf = Lay<6>::NF; *nd = Lay<6>::ND; *ni = Lay<6>::NI; }
   return 0;
 }
 int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng) {
   h->st.f = f; h->st.d = d; h->st.i = i; h->st.rng = (unsigned long long*)rng; return 0;
 }
-int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : fm_field_offset_t<4>(name); }
+int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : (h->hm.n_arms == 4 ? fm_field_offset_t<4>(name) : fm_field_offset_t<6>(name)); }
 long long fm_launch_count(const fm_handle* h) { return h->launches; }
 
 int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream) {
@@ -115,7 +117,8 @@ int fm_ik_policy(fm_handle* h, float* obs, void* stream) {
   if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
   int N = h->cfg.n_envs, od = fm_obs_dim(h), tpb = 64, nb = (N + tpb - 1) / tpb;
   if (h->hm.n_arms == 2) fm_ik_kernel<2><<<nb, tpb, 0, (cudaStream_t)stream>>>(h->d_ik, h->cfg, h->st, obs, od);
-  else fm_ik_kernel<4><<<nb, tpb, 0, (cudaStream_t)stream>>>(h->d_ik, h->cfg, h->st, obs, od);
+  else if (h->hm.n_arms == 4) fm_ik_kernel<4><<<nb, tpb, 0, (cudaStream_t)stream>>>(h->d_ik, h->cfg, h->st, obs, od);
+  else fm_ik_kernel<6><<<nb, tpb, 0, (cudaStream_t)stream>>>(h->d_ik, h->cfg, h->st, obs, od);
   FM_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -131,14 +134,15 @@ static int copy_state_to_host(fm_handle* h, std::vector<float>& f, std::vector<i
 int fm_get_state(fm_handle* h, fm_state_view* v) {
   std::vector<float> f; std::vector<int> iv;
   if (int rc = copy_state_to_host(h, f, iv)) return rc;
-  if (h->hm.n_arms == 2) fm_view_get<2>(f.data(), h->st.n, v); else fm_view_get<4>(f.data(), h->st.n, v);
+  if (h->hm.n_arms == 2) fm_view_get<2>(f.data(), h->st.n, v); else if (h->hm.n_arms == 4) fm_view_get<4>(f.data(), h->st.n, v); else fm_view_get<6>(f.data(), h->st.n, v);
   return 0;
 }
 int fm_set_state(fm_handle* h, const fm_state_view* v) {
   std::vector<float> f; std::vector<int> iv;
   if (int rc = copy_state_to_host(h, f, iv)) return rc;
   if (h->hm.n_arms == 2) { fm_view_set<2>(f.data(), h->st.n, v); fm_view_clear_warm<2>(iv.data(), h->st.n, v->env); }
-  else { fm_view_set<4>(f.data(), h->st.n, v); fm_view_clear_warm<4>(iv.data(), h->st.n, v->env); }
+  else if (h->hm.n_arms == 4) { fm_view_set<4>(f.data(), h->st.n, v); fm_view_clear_warm<4>(iv.data(), h->st.n, v->env); }
+  else { fm_view_set<6>(f.data(), h->st.n, v); fm_view_clear_warm<6>(iv.data(), h->st.n, v->env); }
   FM_CUDA(cudaMemcpy(h->st.f, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
   FM_CUDA(cudaMemcpy(h->st.i, iv.data(), iv.size() * sizeof(int), cudaMemcpyHostToDevice));
   return 0;
@@ -151,7 +155,7 @@ int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void* s
   FM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (view) {
     FM_CUDA(cudaMemcpy(&hd, h->d_dump, sizeof(hd), cudaMemcpyDeviceToHost));
-    if (h->hm.n_arms == 2) fm_dump_to_view<2>(hd, view); else fm_dump_to_view<4>(hd, view);
+    if (h->hm.n_arms == 2) fm_dump_to_view<2>(hd, view); else if (h->hm.n_arms == 4) fm_dump_to_view<4>(hd, view); else fm_dump_to_view<6>(hd, view);
   }
   return 0;
 }

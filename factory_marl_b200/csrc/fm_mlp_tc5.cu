@@ -184,7 +184,7 @@ const char* fm_tc5_last_error(void) { return g_tc5_err.c_str(); }
 int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const void* w1, const void* w2, const void* w3,
                        const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
                        int* status, void* stream) {
-  if (kp % 16 || kp > 512 || (op != 16 && op != 32)) { g_tc5_err = "fm_mlp_forward_tc5: kp % 16 == 0, kp <= 512, op in {16, 32}"; return 1; }
+  if (kp % 16 || kp > 512 || op % 16 || op < 16 || op > 64) { g_tc5_err = "fm_mlp_forward_tc5: kp % 16 == 0, kp <= 512, op in {16, 32, 48, 64}"; return 1; }
   Tc5Args a;
   a.x = x; a.ld_x = ld_x; a.d_in = d_in; a.idx = idx; a.w1 = (const bf16*)w1; a.w2 = (const bf16*)w2; a.w3 = (const bf16*)w3;
   a.b1 = b1; a.b2 = b2; a.b3 = b3; a.out = out; a.op = op; a.h1 = (bf16*)h1; a.h2 = (bf16*)h2; a.n = n; a.kp = kp; a.status = status;

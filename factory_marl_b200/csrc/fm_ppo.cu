@@ -230,8 +230,8 @@ __global__ void ppo_loss_kernel(const float* __restrict__ out_pi, int ldp, const
                                 float* __restrict__ g_log_std, float* __restrict__ stats) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   float pl = 0.f, vl = 0.f, kl = 0.f, cf = 0.f, ent = 0.f;
-  float gls[32];
-  for (int k = 0; k < 32; ++k) gls[k] = 0.f;
+  float gls[64];                           // act_dim <= 64 (six arms: 48)
+  for (int k = 0; k < 64; ++k) gls[k] = 0.f;
   if (r < n) {
     int s = idx ? idx[r] : r;
     float a_hat = adv[s];
@@ -302,7 +302,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ out_pi, int ldp, const
   }
   if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[0], pl / n); atomicAdd(&stats[1], vl / n); atomicAdd(&stats[2], kl / n); atomicAdd(&stats[3], cf / n); atomicAdd(&stats[4], ent / n); }
   if (!discrete)
-    for (int k = 0; k < A && k < 32; ++k) {
+    for (int k = 0; k < A && k < 64; ++k) {
       float v = gls[k];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
       if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&g_log_std[k], v);

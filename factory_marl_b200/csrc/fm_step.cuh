@@ -74,6 +74,7 @@ FM_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 #ifndef FM_ENVS_PAD
 #define FM_ENVS_PAD 1
 #endif
+#define FM_ENVS_PAD6 1
 template <int NA>
 struct EnvS {
   static const int NV = 61 + 9 * NA, NQ = 71 + 9 * NA, NU = 1 + 8 * NA, NNODE = FM_NCUBE + NA;
@@ -143,11 +144,11 @@ struct EnvS {
   int prev_arow_n[NA], prev_arow_code[NA][FM_AROW];
   float prev_arow_f[NA][FM_AROW];
   int c_key[FmCap<NA>::CON];
-  int pad_[FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 2 (mod 32): the envs of a block start on different (even) shared-memory banks,
+  int pad_[NA == 6 ? FM_ENVS_PAD6 : FM_ENVS_PAD];   // sizeof(EnvS) / 4 = 2 (mod 32): the envs of a block start on different (even) shared-memory banks,
                            // and the next item of an odd-stride array falls on the odd ones
 };
 // the envs of a block must start on distinct shared-memory banks: stride = 2 (mod 4) words (checked for both scenes)
-static_assert((sizeof(EnvS<2>) / 4) % 4 == 2 && (sizeof(EnvS<4>) / 4) % 4 == 2, "re-pad EnvS (pad_) after changing its members");
+static_assert((sizeof(EnvS<2>) / 4) % 4 == 2 && (sizeof(EnvS<4>) / 4) % 4 == 2 && (sizeof(EnvS<6>) / 4) % 4 == 2, "re-pad EnvS (pad_) after changing its members");
 
 // flags
 #define FM_FLAG_CON_OVERFLOW 1

@@ -32,6 +32,7 @@ struct Lay {
 struct FmStatePtrs { float* f; double* d; int* i; unsigned long long* rng; int n; float* ws; /* library-owned scratch [n][FmCap<NA>::WS] */ };
 
 // per-env task scratch kept in shared memory next to EnvS
+template <int NA>
 struct TaskS {
   int in_scene[FM_NCUBE], out_scene[FM_NCUBE], n_in, n_out, step_counter, since_spawn, fail, out_counter, score[2], last_score[2], ep_len;
   double conveyor_speed, spawn_freq, play_time;
@@ -39,9 +40,9 @@ struct TaskS {
   int terminated, out_of_reach, force_term, done_prev;
   int stale, index_err;   // see ph_task: dm_control dirty flag at the end of the task step; flagged IndexError case of task_utils.py:110
   int order[FM_NCUBE];
-  float last_gd[FM_MAX_ARMS], last_bd[FM_MAX_ARMS];
-  float site[FM_MAX_ARMS][3];
-  int fsm_state[FM_MAX_ARMS], ignore[FM_MAX_ARMS][FM_MAX_ARMS];
+  float last_gd[NA], last_bd[NA];
+  float site[NA][3];
+  int fsm_state[NA], ignore[NA][NA];
   float act_norm;
 };
 
@@ -68,7 +69,7 @@ FM_HD double pcg64_uniform(unsigned long long* st /*hi, lo, inc_hi, inc_lo*/) {
 
 // ---- load / store between HBM (SoA) and shared memory
 template <int NA, int E>
-FM_PH void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_load(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
@@ -99,7 +100,7 @@ FM_PH void ph_load(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int 
     int e = w % E, k = w / E; int env = env0 + e;
     if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     int v = st.i[(size_t)k * N + env];
-    TaskS& t = TS[e];
+    TaskS<NA>& t = TS[e];
     if (k == L::I_PREV_N) S[e].prev_n = v;
     else if (k >= L::I_PREV_KEY && k < L::I_PREV_AN) S[e].prev_key[k - L::I_PREV_KEY] = v;
     else if (k >= L::I_PREV_AN && k < L::I_PREV_ACODE) S[e].prev_arow_n[k - L::I_PREV_AN] = v;
@@ -147,7 +148,7 @@ FM_PH void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid,
 
 // ---- action map -> ctrl (clipped to actuator_ctrlrange, base_env.py:255-262)
 template <int NA, int E>
-FM_PH void ph_action(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, const float* act_f,
+FM_PH void ph_action(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, const float* act_f,
                      const int* act_i, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
@@ -211,7 +212,7 @@ FM_PH void ph_store_pre(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, i
 }
 
 template <int NA>
-FM_HD void task_hide(EnvS<NA>& s, TaskS& t, int k) {
+FM_HD void task_hide(EnvS<NA>& s, TaskS<NA>& t, int k) {
   t.out_scene[t.n_out++] = k;
   float* q = s.cube_q[k]; float* v = s.cube_v[k];
   q[0] = 5.0f; q[1] = (float)(t.out_counter * 0.2); q[2] = 1.0f; q[3] = 1.f; q[4] = 0.f; q[5] = 0.f; q[6] = 0.f;
@@ -220,10 +221,10 @@ FM_HD void task_hide(EnvS<NA>& s, TaskS& t, int k) {
   t.out_counter++;
 }
 template <int NA>
-FM_HD void task_remove_in(TaskS& t, int idx) { for (int i = idx; i + 1 < t.n_in; ++i) t.in_scene[i] = t.in_scene[i + 1]; t.n_in--; }
+FM_HD void task_remove_in(TaskS<NA>& t, int idx) { for (int i = idx; i + 1 < t.n_in; ++i) t.in_scene[i] = t.in_scene[i + 1]; t.n_in--; }
 
 template <int NA>
-FM_HD void task_reset_state(EnvS<NA>& s, TaskS& t, const FmEnvCfg& cfg) {
+FM_HD void task_reset_state(EnvS<NA>& s, TaskS<NA>& t, const FmEnvCfg& cfg) {
   s.belt_q = 0.f; s.belt_v = 0.f;
   for (int a = 0; a < NA; ++a) for (int d = 0; d < 9; ++d) { s.arm_q[a][d] = 0.f; s.arm_v[a][d] = 0.f; s.arm_qlo(a)[d] = 0.f; }
   for (int k = 0; k < FM_NCUBE; ++k) {
@@ -246,13 +247,13 @@ FM_HD void task_reset_state(EnvS<NA>& s, TaskS& t, const FmEnvCfg& cfg) {
 
 // ---- task manager step + reward + termination (thread per env)
 template <int NA, int E>
-FM_PH void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_task(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   int N = st.n;
   for (int w = tid; w < E; w += T) {
     int env = env0 + w;
     if (env >= N) continue;
-    EnvS<NA>& s = S[w]; TaskS& t = TS[w];
+    EnvS<NA>& s = S[w]; TaskS<NA>& t = TS[w];
     // TaskManager.step (task_utils.py:135-144)
     int spawn_steps = (int)(1.0 / (0.1 * t.spawn_freq));
     bool dirty = false;
@@ -355,7 +356,7 @@ FM_PH void ph_task(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, const FmEnvCfg& 
 }
 
 template <int NA>
-FM_HD float obs_value(const EnvS<NA>& s, const TaskS& t, int j) {
+FM_HD float obs_value(const EnvS<NA>& s, const TaskS<NA>& t, int j) {
   if (j < 24 * NA) {
     int a = j / 24, r = j % 24;
     if (r < 8) return s.arm_q[a][r];
@@ -370,7 +371,7 @@ FM_HD float obs_value(const EnvS<NA>& s, const TaskS& t, int j) {
 
 // write base observation (_get_state + _process_observation, base_env.py:149-175, environments.py:55-82)
 template <int NA, int E>
-FM_PH void ph_obs(EnvS<NA>* S, TaskS* TS, float* obs, int obs_dim, int n_envs, int env0, int tid, int T, bool only_done) {
+FM_PH void ph_obs(EnvS<NA>* S, TaskS<NA>* TS, float* obs, int obs_dim, int n_envs, int env0, int tid, int T, bool only_done) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   const int base = 24 * NA + 130;
   for (int w = tid; w < base * E; w += T) {
@@ -382,7 +383,7 @@ FM_PH void ph_obs(EnvS<NA>* S, TaskS* TS, float* obs, int obs_dim, int n_envs, i
 }
 
 template <int NA, int E>
-FM_PH void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* reward, unsigned char* terminated, int* scores,
+FM_PH void ph_outputs(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, float* reward, unsigned char* terminated, int* scores,
                       unsigned char* flags, float* ep_info, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
@@ -390,7 +391,7 @@ FM_PH void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* rewa
   for (int w = tid; w < E; w += T) {
     int env = env0 + w;
     if (env >= N) continue;
-    TaskS& t = TS[w];
+    TaskS<NA>& t = TS[w];
     if (reward) reward[env] = t.reward;
     if (terminated) terminated[env] = (unsigned char)t.terminated;
     if (scores) { scores[2 * env] = t.score[0]; scores[2 * env + 1] = t.score[1]; }
@@ -404,7 +405,7 @@ FM_PH void ph_outputs(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, float* rewa
 
 // reset (reset_sim base_env.py:177-198 + TaskManager.reset task_utils.py:146-156) for terminated envs when auto-reset is on
 template <int NA, int E>
-FM_PH void ph_reset_done(EnvS<NA>* S, TaskS* TS, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T, const unsigned char* mask) {
+FM_PH void ph_reset_done(EnvS<NA>* S, TaskS<NA>* TS, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T, const unsigned char* mask) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
@@ -421,7 +422,7 @@ FM_PH void ph_reset_done(EnvS<NA>* S, TaskS* TS, const FmEnvCfg& cfg, const FmSt
 }
 
 template <int NA, int E>
-FM_PH void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_store(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
@@ -458,7 +459,7 @@ FM_PH void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
   for (int w = tid; w < L::NI * E; w += T) {
     int e = w % E, k = w / E; int env = env0 + e;
     if (env >= N) continue;
-    TaskS& t = TS[e];
+    TaskS<NA>& t = TS[e];
     int v; bool wr = true;
     if (k < 10) v = t.in_scene[k]; else if (k < 20) v = t.out_scene[k - 10];
     else if (k == L::I_NIN) v = t.n_in; else if (k == L::I_NOUT) v = t.n_out; else if (k == L::I_STEP) v = t.step_counter;
@@ -486,7 +487,7 @@ FM_PH void ph_store(EnvS<NA>* S, TaskS* TS, const FmStatePtrs& st, int env0, int
 
 // gripper site positions (between_gripper_plates, gripper.xml:43) after the final kinematics
 template <int NA, int E>
-FM_PH void ph_site(EnvS<NA>* S, TaskS* TS, const FmDevModel& m, int tid, int T) {
+FM_PH void ph_site(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, int tid, int T) {
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   for (int w = tid; w < NA * E; w += T) {
     int e = w % E, a = w / E;

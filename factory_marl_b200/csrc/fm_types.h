@@ -11,14 +11,14 @@
 #define FM_MAX_SBOX 12      // table + 2 x (bucket floor + 4 fences)
 #define FM_MAXCON 56        // contacts per env
 #define FM_MAXARMSIDE 40    // contact sides that touch an arm (a grasped cube alone makes 16+); stored in global scratch (each stores 3x9 Jacobian + 3x9 Minv J^T)
-#define FM_MAX_ARMS 4
+#define FM_MAX_ARMS 6
 #define FM_MAXCON_ALL 96   // largest per-scene contact capacity (debug dump arrays)
 // per-scene capacities: FM_MAXCON / FM_MAXARMSIDE are the two-arm values; four arms crash into each other and the table far more
 // often (and have the shared memory to spare: one block of 7 envs per SM)
 template <int NA> struct FmCap {
   static constexpr int CON = NA <= 2 ? FM_MAXCON : FM_MAXCON_ALL;         // contacts per env
   static constexpr int ARMSIDE = NA <= 2 ? FM_MAXARMSIDE : 64;            // contact sides on an arm (6-bit slot)
-  static constexpr int QUEUE = NA <= 2 ? 96 : 160;                        // cluster pairs queued for the narrow phase
+  static constexpr int QUEUE = NA <= 2 ? 96 : (NA <= 4 ? 160 : 224);                        // cluster pairs queued for the narrow phase
   static constexpr int NCL = FM_NCUBE + NA * FM_NARMBODY;                 // sphere-bounded broad-phase clusters
   static constexpr int WS = ARMSIDE * 54 + CON * 4 + 1 + 8 * FM_MAX_ARMS + 9 * FM_MAX_ARMS + 4 * NCL; // floats of the env's global scratch row: as_J, as_B, prev_f, ct_d0, arm_qlo, bnd_ref
 };

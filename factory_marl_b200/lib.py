@@ -15,7 +15,7 @@ _lib = None
 
 
 _STEP_HDRS = ["fm_types.h", "fm_math.cuh", "fm_collide.cuh", "fm_step.cuh", "fm_task.cuh", "fm_driver.cuh", "fm_kernel.cuh"]
-_SHAPES = ["2_1", "2_4", "2_14", "2_14n", "4_1", "4_4", "4_7", "4_7n"]        # arms _ envs per block (fm_kernel.cuh); n = with the big-island Newton
+_SHAPES = ["2_1", "2_4", "2_14", "2_14n", "4_1", "4_4", "4_7", "4_7n", "6_1", "6_6", "6_6n"]        # arms _ envs per block (fm_kernel.cuh); n = with the big-island Newton
 _DEPS = {
     "fm_lib.cu": ["fm_lib.cu", "fm_ik.cuh", "fm_host_model.h", "fm_host_common.h", "../../include/fm_api.h", "../../include/fm_blob.h"] + _STEP_HDRS,
     "fm_ppo.cu": ["fm_ppo.cu", "../../include/fm_api.h"],

@@ -78,7 +78,7 @@ class PolicyValueNet:
                 off[(name, which)] = o
                 o += sz
         off["log_std"] = o
-        o += 32
+        o += max(32, (act_dim + 15) // 16 * 16)      # 32 for two and four arms (the layout of round-1 checkpoints), 48 for six
         self.off, self.n_params = off, o
         self.params = torch.zeros(o, dtype=torch.float32, device=self.dev)
         self.params_bf16 = torch.zeros(o, dtype=torch.bfloat16, device=self.dev)

@@ -28,7 +28,7 @@ typedef struct fm_config {
   /* pgs_inner: sweep cap of the PGS islands (0 = 4), pgs_tol: stopping criterion in m/s^2 (0 = 1e-3), pgs_outer: 1 = solve arm + contact
    * islands by Gauss-Seidel sweeps only (0 = the IK-driven classes use the warp-cooperative active-set Newton).
    * envs_per_block: block shape of the step kernel: 0 = by batch size, 1 | 4 = small batches / tests, 14 (two arms) | 7 (four
-   * arms) = one block per SM (default from 2048 envs).  reserved: 1 = keep hidden cubes live (strict mode), 0 = sleep them. */
+   * arms) | 6 (six arms; also stands in for 4 there) = one block per SM (default from 2048 envs).  reserved: 1 = keep hidden cubes live (strict mode), 0 = sleep them. */
   int32_t pgs_outer, pgs_inner, envs_per_block, reserved;
   float pgs_tol, reserved_f;
   double initial_conveyor_speed, conveyor_acceleration, pt_time, force_contact_threshold, control_frequency,
@@ -50,10 +50,10 @@ typedef struct fm_debug_view {
   int32_t env, ncon, flags, reserved;
   int32_t pair[64][2];          /* geom ids (MuJoCo numbering of the compiled scene), sorted */
   float pos[64][3], normal[64][3], force[64][4];
-  float site_xpos[4][3];
-  float mass_matrix[4][45];     /* packed lower triangle of each arm's 9x9 block */
-  float bias[4][9];
-  float qacc_smooth[97], qacc[97];
+  float site_xpos[6][3];
+  float mass_matrix[6][45];     /* packed lower triangle of each arm's 9x9 block */
+  float bias[6][9];
+  float qacc_smooth[115], qacc[115];
 } fm_debug_view;
 
 /* BaseEnv.__init__ + build_scene (base_env.py:15-147, scene.py:109-169): model_blob from factory_marl_b200.model.build_blob */

@@ -52,19 +52,20 @@ static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
   // same rule as the library: the IK-driven classes run the variant with the big-island Newton (here for every block shape)
   const bool bign = h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1;
   HostRun run{32 * TW};
-  size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS)) + 64;
+  size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS<NA>)) + 64;
   if (h->smem.size() < need) h->smem.resize(need);
   int nblk = (h->cfg.n_envs + E - 1) / E;
   for (int b = 0; b < nblk; ++b) {
     memset(h->smem.data(), 0, need);
-    EnvS<NA>* S = (EnvS<NA>*)h->smem.data(); TaskS* TS = (TaskS*)(S + E);
+    EnvS<NA>* S = (EnvS<NA>*)h->smem.data(); TaskS<NA>* TS = (TaskS<NA>*)(S + E);
     if (bign) fm_block_step<NA, E, TW, true>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
     else fm_block_step<NA, E, TW, false>(run, S, TS, h->hm.dm, h->hm.cpairs.data(), h->hm.geom_class.data(), h->cfg, h->st, ar, b * E);
   }
 }
 static void dispatch(fm_handle* h, const FmStepArgs& ar) {
   if (h->hm.n_arms == 2) { if (h->E == 1) run_blocks<2, 1>(h, ar); else if (h->E == 2) run_blocks<2, 2>(h, ar); else if (h->E == 7) run_blocks<2, 7>(h, ar); else if (h->E == 14) run_blocks<2, 14, 12>(h, ar); else run_blocks<2, 4>(h, ar); }
-  else { if (h->E == 1) run_blocks<4, 1>(h, ar); else if (h->E == 7) run_blocks<4, 7, 7>(h, ar); else run_blocks<4, 4>(h, ar); }
+  else if (h->hm.n_arms == 4) { if (h->E == 1) run_blocks<4, 1>(h, ar); else if (h->E == 7) run_blocks<4, 7, 7>(h, ar); else run_blocks<4, 4>(h, ar); }
+  else { if (h->E == 1) run_blocks<6, 1>(h, ar); else run_blocks<6, 6, 8>(h, ar); }
 }
 
 // randomised equivalence check of the box-on-face fast path against the general separating-axis routine
@@ -109,23 +110,23 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     fm_handle* h = new fm_handle();
     fm_build_host_model(blob, n, h->hm);
     if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
-    if (h->hm.n_arms != 2 && h->hm.n_arms != 4) throw std::runtime_error("only num_arms 2 or 4");
+    if (h->hm.n_arms != 2 && h->hm.n_arms != 4 && h->hm.n_arms != 6) throw std::runtime_error("num_arms must be 2, 4 or 6");
     h->user = *cfg; h->cfg = fm_make_cfg(*cfg, h->hm.timestep);
-    { int e = cfg->envs_per_block; h->E = (e == 1 || e == 7 || (cfg->n_arms == 2 && (e == 2 || e == 14))) ? e : 4; }   // same shapes as the library (+ E = 2)
-    h->ws.assign(((size_t)cfg->n_envs + 32) * (cfg->n_arms == 2 ? FmCap<2>::WS : FmCap<4>::WS), 0.f);
+    { int e = cfg->envs_per_block; h->E = (e == 1 || e == 7 || (cfg->n_arms == 2 && (e == 2 || e == 14))) ? e : 4; if (cfg->n_arms == 6 && h->E != 1) h->E = 6; }   // same shapes as the library (+ E = 2)
+    h->ws.assign(((size_t)cfg->n_envs + 32) * (cfg->n_arms == 2 ? FmCap<2>::WS : (cfg->n_arms == 4 ? FmCap<4>::WS : FmCap<6>::WS)), 0.f);
     h->st = FmStatePtrs{nullptr, nullptr, nullptr, nullptr, cfg->n_envs, h->ws.data()};
     *out = h; return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 int fm_destroy(fm_handle* h) { delete h; return 0; }
-int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : Lay<4>::obs_dim(h->cfg.env_class); }
+int fm_obs_dim(const fm_handle* h) { return h->hm.n_arms == 2 ? Lay<2>::obs_dim(h->cfg.env_class) : (h->hm.n_arms == 4 ? Lay<4>::obs_dim(h->cfg.env_class) : Lay<6>::obs_dim(h->cfg.env_class)); }
 int fm_act_dim(const fm_handle* h) { return fm_act_dim_of(h->cfg.env_class, h->hm.n_arms); }
 int fm_state_rows(const fm_handle* h, int32_t* nf, int32_t* nd, int32_t* ni) {
-  if (h->hm.n_arms == 2) { *nf = Lay<2>::NF; *nd = Lay<2>::ND; *ni = Lay<2>::NI; } else { *nf = Lay<4>::NF; *nd = Lay<4>::ND; *ni = Lay<4>::NI; }
+  if (h->hm.n_arms == 2) { *nf = Lay<2>::NF; *nd = Lay<2>::ND; *ni = Lay<2>::NI; } else if (h->hm.n_arms == 4) { *nf = Lay<4>::NF; *nd = Lay<4>::ND; *ni = Lay<4>::NI; } else { *nf = Lay<6>::NF; *nd = Lay<6>::ND; *ni = Lay<6>::NI; }
   return 0;
 }
 int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng) { h->st.f = f; h->st.d = d; h->st.i = i; h->st.rng = (unsigned long long*)rng; return 0; }
-int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : fm_field_offset_t<4>(name); }
+int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : (h->hm.n_arms == 4 ? fm_field_offset_t<4>(name) : fm_field_offset_t<6>(name)); }
 int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void*) {
   FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.reset_mask = mask; ar.obs = obs;
   dispatch(h, ar); return 0;
@@ -141,21 +142,23 @@ int fm_ik_policy(fm_handle* h, float* obs, void*) {
   int N = h->cfg.n_envs, od = fm_obs_dim(h);
   for (int e = 0; e < N; ++e) {
     if (h->hm.n_arms == 2) fm_ik_env<2>(h->hm.ik, h->cfg, h->st, obs, od, e);
-    else fm_ik_env<4>(h->hm.ik, h->cfg, h->st, obs, od, e);
+    else if (h->hm.n_arms == 4) fm_ik_env<4>(h->hm.ik, h->cfg, h->st, obs, od, e);
+    else fm_ik_env<6>(h->hm.ik, h->cfg, h->st, obs, od, e);
   }
   return 0;
 }
-int fm_get_state(fm_handle* h, fm_state_view* v) { if (h->hm.n_arms == 2) fm_view_get<2>(h->st.f, h->st.n, v); else fm_view_get<4>(h->st.f, h->st.n, v); return 0; }
+int fm_get_state(fm_handle* h, fm_state_view* v) { if (h->hm.n_arms == 2) fm_view_get<2>(h->st.f, h->st.n, v); else if (h->hm.n_arms == 4) fm_view_get<4>(h->st.f, h->st.n, v); else fm_view_get<6>(h->st.f, h->st.n, v); return 0; }
 int fm_set_state(fm_handle* h, const fm_state_view* v) {
   if (h->hm.n_arms == 2) { fm_view_set<2>(h->st.f, h->st.n, v); fm_view_clear_warm<2>(h->st.i, h->st.n, v->env); }
-  else { fm_view_set<4>(h->st.f, h->st.n, v); fm_view_clear_warm<4>(h->st.i, h->st.n, v->env); }
+  else if (h->hm.n_arms == 4) { fm_view_set<4>(h->st.f, h->st.n, v); fm_view_clear_warm<4>(h->st.i, h->st.n, v->env); }
+  else { fm_view_set<6>(h->st.f, h->st.n, v); fm_view_clear_warm<6>(h->st.i, h->st.n, v->env); }
   return 0;
 }
 int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void*) {
   FmDebugDump* d = new FmDebugDump(); memset(d, 0, sizeof(*d)); d->env = view ? view->env : -1;
   FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? d : nullptr;
   dispatch(h, ar);
-  if (view) { if (h->hm.n_arms == 2) fm_dump_to_view<2>(*d, view); else fm_dump_to_view<4>(*d, view); }
+  if (view) { if (h->hm.n_arms == 2) fm_dump_to_view<2>(*d, view); else if (h->hm.n_arms == 4) fm_dump_to_view<4>(*d, view); else fm_dump_to_view<6>(*d, view); }
   delete d; return 0;
 }
 }

@@ -53,6 +53,19 @@ def test_golden_rollouts_4arms():
     pc.case_golden_rollouts(BE, 4, ["AllFullRLProgressRewardEnv", "PauseIKToggleEnv"])
 
 
+def test_single_substep_free_6arms():
+    """scene.py:114,153-158: table length 2.0, buckets at y = -1.3, arms 4 and 5 at (+-0.63, 0.7)"""
+    pc.case_single_substep_free(BE, 6)
+
+
+def test_golden_rollouts_6arms():
+    pc.case_golden_rollouts(BE, 6, ["AllFullRLProgressRewardEnv", "PauseIKToggleEnv", "FactoryManipulationEnv"])
+
+
+def test_golden_rollouts_6arms_block_of_6():
+    pc.case_golden_rollouts(BE, 6, ["SingleDeltaProgressRewardEnv", "BackupIKToggleEnv"], envs_per_block=6)
+
+
 def test_contact_free_100_step_rollout():
     pc.case_contact_free_100_steps(BE)
 

@@ -63,6 +63,38 @@ def test_golden_rollouts_4arms():
     pc.case_golden_rollouts(BE, 4)
 
 
+def test_single_substep_free_6arms():
+    pc.case_single_substep_free(BE, 6)
+
+
+def test_golden_rollouts_6arms():
+    """num_arms = 6 (scene.py:114,153-158): every env class, default shape (one env per block below 2048 envs -> block of 6)"""
+    pc.case_golden_rollouts(BE, 6)
+
+
+def test_golden_rollouts_6arms_one_env_per_block():
+    pc.case_golden_rollouts(BE, 6, ["AllFullRLProgressRewardEnv", "PauseIKToggleEnv"], envs_per_block=1)
+
+
+def test_six_arm_vec_env_steps_with_ik_toggling():
+    """six arms through the VecEnv mirror: spaces, 2048 envs (the block-of-6 shape with a ragged last block), 30 steps of random
+    toggles with auto-reset; capacity flags stay rare and episodes end"""
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    n = 2050
+    env = FactoryVecEnv("PauseIKToggleEnv", num_envs=n, num_arms=6, seeds=list(range(42, 42 + n)))
+    assert env.observation_space.shape == (322,) and list(env.action_space.nvec) == [2] * 6
+    obs = env.reset()
+    assert obs.shape == (n, 322) and bool(torch.isfinite(obs).all())
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(30):
+        a = torch.randint(0, 2, (n, 6), device="cuda", generator=gen, dtype=torch.int32)
+        obs, rew, term, _ = env.step(a, with_infos=False)
+    assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+    flags = env.core.i[env.core.off("I_FLAGS")]
+    assert float(((flags & 15) != 0).float().mean()) < 0.05
+    assert int(env.monitor.ring_head.item()) > 0                 # six arms in 2 m of table: force terminations are frequent
+
+
 def test_contact_free_100_step_rollout():
     pc.case_contact_free_100_steps(BE)
 
@@ -111,7 +143,7 @@ def test_full_size_properties_4096_envs():
     assert env.gpu_launches >= 13
 
 
-@pytest.mark.parametrize("n_arms,shapes", [(2, (1, 4, 14)), (4, (4, 7))])
+@pytest.mark.parametrize("n_arms,shapes", [(2, (1, 4, 14)), (4, (4, 7)), (6, (1, 6))])
 def test_block_shapes_agree(n_arms, shapes):
     """every block shape built into the library (envs per block / warps per block) steps the same env to the same result;
     17 envs leave a ragged last block whose padding slots must not leak"""

@@ -24,7 +24,7 @@ def _torch_nets(pol):
     return sd, fwd
 
 
-@pytest.mark.parametrize("obs_dim,act_dim,discrete", [(178, 16, False), (258, 4, True)])
+@pytest.mark.parametrize("obs_dim,act_dim,discrete", [(178, 16, False), (258, 4, True), (274, 48, False), (322, 6, True)])
 def test_policy_forward_matches_fp32(obs_dim, act_dim, discrete):
     from factory_marl_b200.ppo import PolicyValueNet
     pol = PolicyValueNet(obs_dim, act_dim, discrete, seed=3, capacity=512)
@@ -70,11 +70,12 @@ def test_gae_matches_sb3_recurrence():
     assert np.abs(adv.cpu().numpy() - A).max() < 1e-4 and np.abs(ret.cpu().numpy() - (A + v)).max() < 1e-4
 
 
-@pytest.mark.parametrize("discrete", [False, True])
+@pytest.mark.parametrize("discrete", [False, True, "six_arms"])
 def test_ppo_update_gradients_match_autograd(discrete):
     import ctypes as C
     from factory_marl_b200.ppo import PolicyValueNet
-    D, A, n = (258, 4, 1024) if discrete else (178, 16, 1024)
+    D, A, n = (258, 4, 1024) if discrete is True else ((274, 48, 1024) if discrete == "six_arms" else (178, 16, 1024))
+    discrete = discrete is True
     pol = PolicyValueNet(D, A, discrete, seed=5, capacity=n)
     sd, _ = _torch_nets(pol)
     if not discrete:
@@ -160,7 +161,21 @@ def test_ppo_learn_smoke_and_sb3_roundtrip(tmp_path):
         assert torch.equal(v, sd[k])
 
 
-@pytest.mark.parametrize("obs_dim,act_dim,discrete", [(178, 16, False), (258, 4, True), (226, 32, False)])
+def test_ppo_learn_six_arms():
+    """num_arms = 6: 274-dim observations, 48-dim Box actions through rollout (tcgen05 forward, N = 48) and update"""
+    from factory_marl_b200.ppo import PPO
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    env = FactoryVecEnv("AllFullRLProgressRewardEnv", num_envs=128, num_arms=6, gripper_to_closest_cube_reward_factor=0.2,
+                        closest_cube_to_bucket_reward_factor=0.4, base_reward=0.4)
+    algo = PPO(env, n_steps=4, batch_size=256, n_epochs=2)
+    p0 = algo.pol.params.clone()
+    algo.learn(2 * 4 * 128)
+    assert algo.pol.adam_step == 2 * 2 * 2 and not torch.equal(p0, algo.pol.params) and torch.isfinite(algo.pol.params).all()
+    sd = algo.pol.sb3_state_dict()
+    assert sd["mlp_extractor.policy_net.0.weight"].shape == (128, 274) and sd["action_net.weight"].shape == (48, 128) and sd["log_std"].shape == (48,)
+
+
+@pytest.mark.parametrize("obs_dim,act_dim,discrete", [(178, 16, False), (258, 4, True), (226, 32, False), (274, 48, False), (322, 6, True)])
 def test_tcgen05_mlp_matches_mma_sync_and_fp32(obs_dim, act_dim, discrete):
     """The fused tcgen05 forward (TMEM accumulators) against the mma.sync GEMM chain and a fp32 torch MLP."""
     from factory_marl_b200.ppo import PolicyValueNet

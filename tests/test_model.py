@@ -8,11 +8,23 @@ from factory_marl_b200._capi import pcg64_state_words
 
 
 def test_sizes_match_survey_a1():
-    for n, (nb, ng, nq, nv, nu) in {2: (54, 163, 89, 79, 17), 4: (82, 303, 107, 97, 33)}.items():
+    for n, (nb, ng, nq, nv, nu) in {2: (54, 163, 89, 79, 17), 4: (82, 303, 107, 97, 33), 6: (110, 443, 125, 115, 49)}.items():
         M = fm.build_model(n)
         assert tuple(M["sizes"][[0, 1, 3, 4, 5]]) == (nb, ng, nq, nv, nu)
-        assert int((M["geom_collide"] == 1).sum()) == {2: 133, 4: 243}[n]
+        assert int((M["geom_collide"] == 1).sum()) == {2: 133, 4: 243, 6: 353}[n]
         assert int((M["geom_arm"] >= 0).sum()) == 70 * n            # base_env.py:121-126: 61 + 9 geoms per arm
+
+
+def test_six_arm_scene_layout():
+    """scene.py:114 table length 1 + 0.5 (n - 2) / 2, :140 bucket y = 0.7 - (n // 2 - 1), :153-158 arms 4 and 5 sit between the rows
+    at 0.9 x the lateral offset"""
+    M = fm.build_model(6)
+    exp = [(0.7, -2.0), (-0.7, -2.0), (0.7, -0.6), (-0.7, -0.6), (0.63, 0.7), (-0.63, 0.7)]
+    assert np.allclose(M["arm_base_pos"][:, :2], exp, atol=1e-12) and np.allclose(M["arm_base_pos"][:, 2], 1.0)
+    bucket_floor = M["geom_body"][M["bucket_geom"]]
+    assert np.allclose(sorted(M["body_pos"][bucket_floor][:, 0]), [-0.9, 0.9]) and np.allclose(M["body_pos"][bucket_floor][:, 1], 0.7 - 2)
+    from oracle.oracle_py import Oracle
+    o = Oracle(fm.build_blob(6)); o.env_create("PauseIKToggleEnv"); assert len(o.env_reset()) == 6 * 24 + 130 + 48
 
 
 def test_cube_sizes_scene_seed_42(model2):

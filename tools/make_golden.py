@@ -29,7 +29,8 @@ def actions_for(cls, n_arms, steps, rng):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for n_arms in (2, 4):
+    arms = tuple(int(a) for a in sys.argv[1:]) or (2, 4, 6)       # python tools/make_golden.py 6: only the six-arm scene
+    for n_arms in arms:
         blob = fm.build_blob(n_arms)
         for cls in ENV_CLASSES:
             steps = 12 if n_arms == 2 else 6
@@ -48,6 +49,8 @@ def main():
                                 reward=np.array(rew), terminated=np.array(term), scores=np.array(scores, np.int32),
                                 qpos=np.array(qpos), qvel=np.array(qvel))
             print(cls, n_arms, "ok", np.array(obs).shape)
+    if 2 not in arms:
+        return
     # known-answer scalars
     blob = fm.build_blob(2)
     o = Oracle(blob); o.env_create("AllFullRLProgressRewardEnv")
