@@ -320,16 +320,18 @@ __global__ void colsum_kernel(const bf16* __restrict__ d, int n, int ld, int col
 }
 
 // global-norm clip + Adam (torch.optim.Adam semantics, eps 1e-5 from policy.optimizer.pth) + refresh of the bf16 copy.
-// Two launches over the ~1e5 parameters: squared-norm partial sums into norm2[0] (zeroed by a memset node before), then the update.
+// Two launches over the ~1e5 parameters: the squared norm into norm2[0], then the update.
 #define FM_ADAM_BLOCKS 64
-__global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict__ g, int n, float grad_scale, float* __restrict__ norm2) {
-  __shared__ float red[256];
+// ONE block, fixed summation order: with several ranks every replica must compute bit-identical clip factors from the all-reduced
+// gradient (an atomicAdd of per-block partial sums differs in the last bit from run to run and lets the replicas drift apart)
+__global__ void __launch_bounds__(1024) grad_norm_kernel(const float* __restrict__ g, int n, float grad_scale, float* __restrict__ norm2) {
+  __shared__ float red[1024];
   float s = 0.f;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) { float x = g[i] * grad_scale; s += x * x; }
+  for (int i = threadIdx.x; i < n; i += 1024) { float x = g[i] * grad_scale; s += x * x; }
   red[threadIdx.x] = s;
   __syncthreads();
-  for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
-  if (threadIdx.x == 0) atomicAdd(norm2, red[0]);
+  for (int k = 512; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) norm2[0] = red[0];
 }
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, bf16* __restrict__ pb, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float max_norm,
@@ -472,7 +474,7 @@ int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, floa
   if (!stats) { g_ppo_err = "fm_adam_step: stats (8 floats on the device) is required"; return 1; }
   float* norm2 = stats + 6;
   PPO_CUDA(cudaMemsetAsync(norm2, 0, sizeof(float), s));
-  grad_norm_kernel<<<FM_ADAM_BLOCKS, 256, 0, s>>>(net->grads, net->n_params, grad_scale, norm2);
+  grad_norm_kernel<<<1, 1024, 0, s>>>(net->grads, net->n_params, grad_scale, norm2);
   adam_kernel<<<FM_ADAM_BLOCKS, 256, 0, s>>>(net->params, net->params_bf16, net->grads, net->adam_m, net->adam_v, net->n_params, lr, beta1, beta2, eps,
                                              max_grad_norm, grad_scale, step, norm2, stats);
   adam_count_kernel<<<1, 1, 0, s>>>(step, norm2, stats);
