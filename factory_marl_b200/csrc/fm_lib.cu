@@ -50,11 +50,8 @@ static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
 extern "C" {
 const char* fm_last_error(void) { return g_err.c_str(); }
 
-int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {
-  try {
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: this library has no CPU path"; return 3; }
-    fm_handle* h = new fm_handle();
+int fm_destroy(fm_handle* h);
+static int fm_create_impl(const fm_config* cfg, const void* blob, size_t n, fm_handle* h) {
     fm_build_host_model(blob, n, h->hm);
     if (cfg->n_arms != h->hm.n_arms) throw std::runtime_error("cfg.n_arms does not match the model blob");
     if (h->hm.n_arms != 2 && h->hm.n_arms != 4 && h->hm.n_arms != 6) throw std::runtime_error("num_arms must be 2, 4 or 6 (scene.py:148-158)");
@@ -80,9 +77,17 @@ int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out)
     FM_CUDA(cudaMalloc(&h->d_ws, ws_rows * ws_floats * sizeof(float)));
     FM_CUDA(cudaMemset(h->d_ws, 0, ws_rows * ws_floats * sizeof(float)));
     h->st.ws = h->d_ws;
-    *out = h;
     return 0;
-  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+int fm_create(const fm_config* cfg, const void* blob, size_t n, fm_handle** out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: this library has no CPU path"; return 3; }
+  fm_handle* h = new fm_handle();
+  int rc;
+  try { rc = fm_create_impl(cfg, blob, n, h); } catch (const std::exception& e) { g_err = e.what(); rc = 1; }
+  if (rc) { fm_destroy(h); return rc; }          // frees whatever was allocated before the failure
+  *out = h;
+  return 0;
 }
 int fm_destroy(fm_handle* h) {
   if (!h) return 0;
@@ -131,13 +136,20 @@ static int copy_state_to_host(fm_handle* h, std::vector<float>& f, std::vector<i
   FM_CUDA(cudaMemcpy(iv.data(), h->st.i, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
+static int check_env(const fm_handle* h, int env, const char* who) {
+  if (env < 0 || env >= h->st.n) { g_err = std::string(who) + ": env index out of range"; return 1; }
+  if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
+  return 0;
+}
 int fm_get_state(fm_handle* h, fm_state_view* v) {
+  if (int rc = check_env(h, v->env, "fm_get_state")) return rc;
   std::vector<float> f; std::vector<int> iv;
   if (int rc = copy_state_to_host(h, f, iv)) return rc;
   if (h->hm.n_arms == 2) fm_view_get<2>(f.data(), h->st.n, v); else if (h->hm.n_arms == 4) fm_view_get<4>(f.data(), h->st.n, v); else fm_view_get<6>(f.data(), h->st.n, v);
   return 0;
 }
 int fm_set_state(fm_handle* h, const fm_state_view* v) {
+  if (int rc = check_env(h, v->env, "fm_set_state")) return rc;
   std::vector<float> f; std::vector<int> iv;
   if (int rc = copy_state_to_host(h, f, iv)) return rc;
   if (h->hm.n_arms == 2) { fm_view_set<2>(f.data(), h->st.n, v); fm_view_clear_warm<2>(iv.data(), h->st.n, v->env); }
@@ -148,6 +160,7 @@ int fm_set_state(fm_handle* h, const fm_state_view* v) {
   return 0;
 }
 int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void* stream) {
+  if (view) if (int rc = check_env(h, view->env, "fm_debug_substeps")) return rc;
   FmDebugDump hd; memset(&hd, 0, sizeof(hd)); hd.env = view ? view->env : -1;
   FM_CUDA(cudaMemcpy(h->d_dump, &hd, sizeof(hd), cudaMemcpyHostToDevice));
   FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? h->d_dump : nullptr;

@@ -189,11 +189,9 @@ int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const
   a.x = x; a.ld_x = ld_x; a.d_in = d_in; a.idx = idx; a.w1 = (const bf16*)w1; a.w2 = (const bf16*)w2; a.w3 = (const bf16*)w3;
   a.b1 = b1; a.b2 = b2; a.b3 = b3; a.out = out; a.op = op; a.h1 = (bf16*)h1; a.h2 = (bf16*)h2; a.n = n; a.kp = kp; a.status = status;
   size_t smem = (size_t)2 * 128 * (kp > 128 ? kp : 128) * 2;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {  // the opt-in is per device and this process may drive several: set it on every launch (a host-side table look-up)
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 512 * 2);
     if (e != cudaSuccess) { g_tc5_err = cudaGetErrorString(e); return 2; }
-    attr = smem;
   }
   mlp_tc5_kernel<<<(n + 127) / 128, 128, smem, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();

@@ -73,6 +73,10 @@ int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream);
  * bits 2..5 capacity overflow diagnostics, bit 6 = the IndexError case of task_utils.py:110 (skipped); ep_info [N,4] = episode return, length, score0, score1 (Monitor + ep_score_history) */
 int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores,
             uint8_t* flags, float* terminal_obs, float* ep_info, void* stream);
+/* terminal_obs: rows of the envs that terminated in this step hold the observation BEFORE the auto-reset (SB3's
+ * infos[i]["terminal_observation"]); for the toggling classes its IK-proposal tail (last 8 * n_arms entries) is left at zero:
+ * the reference computes it with one more IK solve on the terminal state, which nothing on the path reads (no time-limit
+ * truncation, so SB3 never bootstraps from it). */
 /* IK base policy for all arms: IKPolicy.act + FactoryManipulationEnv._compose_control (ik_policy.py:141-282,
  * environments.py:104-127).  Writes the proposals into the state (used by the next fm_step) and, for the toggling
  * envs, into obs[:, base_dim:] (IKTogglingEnv._process_observation, environments.py:560-577). */

@@ -147,7 +147,7 @@ int fm_ik_policy(fm_handle* h, float* obs, void*) {
   }
   return 0;
 }
-int fm_get_state(fm_handle* h, fm_state_view* v) { if (h->hm.n_arms == 2) fm_view_get<2>(h->st.f, h->st.n, v); else if (h->hm.n_arms == 4) fm_view_get<4>(h->st.f, h->st.n, v); else fm_view_get<6>(h->st.f, h->st.n, v); return 0; }
+int fm_get_state(fm_handle* h, fm_state_view* v) { if (v->env < 0 || v->env >= h->st.n) { g_err = "fm_get_state: env index out of range"; return 1; } if (h->hm.n_arms == 2) fm_view_get<2>(h->st.f, h->st.n, v); else if (h->hm.n_arms == 4) fm_view_get<4>(h->st.f, h->st.n, v); else fm_view_get<6>(h->st.f, h->st.n, v); return 0; }
 int fm_set_state(fm_handle* h, const fm_state_view* v) {
   if (h->hm.n_arms == 2) { fm_view_set<2>(h->st.f, h->st.n, v); fm_view_clear_warm<2>(h->st.i, h->st.n, v->env); }
   else if (h->hm.n_arms == 4) { fm_view_set<4>(h->st.f, h->st.n, v); fm_view_clear_warm<4>(h->st.i, h->st.n, v->env); }

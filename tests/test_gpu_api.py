@@ -145,6 +145,21 @@ def test_reference_policy_pth_roundtrip(run, tmp_path):
         assert np.array_equal(pol.sb3_state_dict()["action_net.weight"].numpy(), w["action_net.weight"])
 
 
+def test_state_views_reject_an_env_index_out_of_range():
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    env = FactoryVecEnv("PauseIKToggleEnv", num_envs=4, num_arms=2)
+    env.reset()
+    for bad in (4, -1):
+        with pytest.raises(RuntimeError, match="out of range"):
+            env.core.get_state(bad)
+        with pytest.raises(RuntimeError, match="out of range"):
+            env.core.set_state(bad, qpos=np.zeros(89))
+        with pytest.raises(RuntimeError, match="out of range"):
+            env.core.debug_substeps(1, env=bad)
+    q, v, c = env.core.get_state(3)
+    assert q.shape == (89,)
+
+
 def test_dump_trajectory_layout(tmp_path):
     from factory_marl_b200.vec_env import dump_trajectory
     env = _env(4, "PauseIKToggleEnv")
