@@ -60,7 +60,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 struct Tc5Args {
   const float* x; int ld_x; int d_in;       // fp32 observations [n, d_in]
   const int* idx;                            // optional row gather
-  const bf16* w1; const bf16* w2; const bf16* w3;      // [Kp,128], [128,128], [128,Op] row-major bf16
+  const bf16* w1; const bf16* w2; const bf16* w3;      // [Kp,128], [128,128], [128,Op] in the packed B-operand image (load_b)
   const float* b1; const float* b2; const float* b3;
   float* out; int op;                        // fp32 [n, op]
   bf16* h1; bf16* h2;                        // optional activations [n,128] (training forward), may be null
@@ -68,16 +68,13 @@ struct Tc5Args {
   int* status;                               // set to 1 on an mbarrier timeout
 };
 
-// B operand: Bt(n_row, k) = W[k][n_row], W row-major [K, N_total] bf16
-__device__ __forceinline__ void load_b(unsigned char* sB, const bf16* __restrict__ W, int K, int N, int rows) {
-  const int nch = K >> 3;
-  for (int i = threadIdx.x; i < rows * nch; i += blockDim.x) {
-    int nr = i % rows, kc = i / rows;
-    __align__(16) bf16 v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = nr < N ? W[(size_t)(8 * kc + q) * N + nr] : __float2bfloat16(0.f);
-    *reinterpret_cast<uint4*>(sB + chunk_off(nr, kc, rows)) = *reinterpret_cast<const uint4*>(v);
-  }
+// B operand: the caller passes the weights already in the shared-memory image (16-byte chunks [K / 8][rows][8 consecutive k],
+// fm_ppo.cu pack_weights_kernel), so staging is a straight coalesced 16-byte copy
+__device__ __forceinline__ void load_b(unsigned char* sB, const bf16* __restrict__ Wp, int K, int rows) {
+  const int nchunk = (K >> 3) * rows;
+  const uint4* src = reinterpret_cast<const uint4*>(Wp);
+  uint4* dst = reinterpret_cast<uint4*>(sB);
+  for (int i = threadIdx.x; i < nchunk; i += blockDim.x) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(128, 1) mlp_tc5_kernel(Tc5Args a) {
@@ -114,7 +111,7 @@ __global__ void __launch_bounds__(128, 1) mlp_tc5_kernel(Tc5Args a) {
       *reinterpret_cast<uint4*>(sA + chunk_off(r, kc, 128)) = *reinterpret_cast<const uint4*>(v);
     }
   }
-  load_b(sB, a.w1, kp, 128, 128);
+  load_b(sB, a.w1, kp, 128);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -164,7 +161,7 @@ __global__ void __launch_bounds__(128, 1) mlp_tc5_kernel(Tc5Args a) {
       // the accumulator has been drained and sA rewritten: stage the next weights, then hand over to the tensor core again
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
-      if (layer == 0) load_b(sB, a.w2, 128, 128, 128); else load_b(sB, a.w3, 128, a.op, a.op);
+      if (layer == 0) load_b(sB, a.w2, 128, 128); else load_b(sB, a.w3, 128, a.op);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
@@ -184,13 +181,13 @@ const char* fm_tc5_last_error(void) { return g_tc5_err.c_str(); }
 int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const void* w1, const void* w2, const void* w3,
                        const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
                        int* status, void* stream) {
-  if (kp % 16 || kp > 512 || op % 16 || op < 16 || op > 64) { g_tc5_err = "fm_mlp_forward_tc5: kp % 16 == 0, kp <= 512, op in {16, 32, 48, 64}"; return 1; }
+  if (kp % 16 || kp > 448 || op % 16 || op < 16 || op > 64) { g_tc5_err = "fm_mlp_forward_tc5: kp % 16 == 0, kp <= 448, op in {16, 32, 48, 64}"; return 1; }
   Tc5Args a;
   a.x = x; a.ld_x = ld_x; a.d_in = d_in; a.idx = idx; a.w1 = (const bf16*)w1; a.w2 = (const bf16*)w2; a.w3 = (const bf16*)w3;
   a.b1 = b1; a.b2 = b2; a.b3 = b3; a.out = out; a.op = op; a.h1 = (bf16*)h1; a.h2 = (bf16*)h2; a.n = n; a.kp = kp; a.status = status;
   size_t smem = (size_t)2 * 128 * (kp > 128 ? kp : 128) * 2;
   {  // the opt-in is per device and this process may drive several: set it on every launch (a host-side table look-up)
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 512 * 2);
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_tc5_err = cudaGetErrorString(e); return 2; }
   }
   mlp_tc5_kernel<<<(n + 127) / 128, 128, smem, (cudaStream_t)stream>>>(a);

@@ -20,7 +20,7 @@ extern "C" int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int*
                                   const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
                                   int* status, void* stream);
 extern "C" const char* fm_tc5_last_error(void);
-static int g_use_tc5 = 1;     // rollout forward on the tcgen05 path (fm_mlp_tc5.cu); 0 = the mma.sync GEMM chain
+static int g_use_tc5 = 3;     // bit 0: rollout forward on the tcgen05 path (fm_mlp_tc5.cu), bit 1: the update's forward too; 0 = mma.sync GEMM chain
 extern "C" void fm_ppo_use_tcgen05(int on) { g_use_tc5 = on; }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -126,6 +126,7 @@ struct fm_ppo_net {
   bf16* params_bf16;    // bf16 copy used by the GEMMs
   float* grads;         // fp32 [n_params]
   float* adam_m; float* adam_v;
+  bf16* params_pk;      // the weight matrices once more, in the shared-memory image of the tcgen05 B operand (pack_weights_kernel)
 };
 
 struct fm_ppo_ws {       // caller-allocated workspace for up to `cap` rows
@@ -326,8 +327,18 @@ __global__ void colsum_kernel(const bf16* __restrict__ d, int n, int ld, int col
 // gradient (an atomicAdd of per-block partial sums differs in the last bit from run to run and lets the replicas drift apart)
 __global__ void __launch_bounds__(1024) grad_norm_kernel(const float* __restrict__ g, int n, float grad_scale, float* __restrict__ norm2) {
   __shared__ float red[1024];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) { float x = g[i] * grad_scale; s += x * x; }
+  // 16-byte loads, eight in flight per thread: ~9e4 parameters are 22 float4 per thread (a scalar dependent loop took ~150 us)
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const int n4 = n >> 2;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < n4; i += 1024) {
+    const float4 v = g4[i];
+    const float a = v.x * grad_scale, b = v.y * grad_scale, c = v.z * grad_scale, d = v.w * grad_scale;
+    s0 += a * a; s1 += b * b; s2 += c * c; s3 += d * d;
+  }
+  float s = (s0 + s1) + (s2 + s3);
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += 1024) { const float x = g[i] * grad_scale; s += x * x; }
   red[threadIdx.x] = s;
   __syncthreads();
   for (int k = 512; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
@@ -355,6 +366,34 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, bf16* 
 __global__ void adam_count_kernel(int step, const float* __restrict__ norm2, float* __restrict__ stats) {
   stats[5] = sqrtf(norm2[0]);
   if (step <= 0) stats[7] = stats[7] + 1.f;
+}
+// tcgen05 B operand of a layer (fm_mlp_tc5.cu): 16-byte chunks [K / 8][N rows][8 consecutive k] — the fused MLP kernel copies this
+// image into shared memory with plain 16-byte loads instead of gathering W[k][n] element by element in every CTA.  One thread per
+// chunk over the six weight matrices; runs after every parameter change (Adam step, state-dict load).
+__global__ void pack_weights_kernel(fm_ppo_net net) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int which = 0; which < 2; ++which) {
+    const int op = which == 0 ? net.out_pad : 16;
+    const int K[3] = {net.obs_pad, 128, 128}, N[3] = {128, 128, op}, off[3] = {net.w1[which], net.w2[which], net.w3[which]};
+    for (int l = 0; l < 3; ++l) {
+      const int nchunk = (K[l] >> 3) * N[l];
+      if (t < nchunk) {
+        const int kc = t / N[l], nr = t % N[l];
+        __align__(16) bf16 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = net.params_bf16[off[l] + (size_t)(8 * kc + q) * N[l] + nr];
+        *reinterpret_cast<uint4*>(net.params_pk + off[l] + (size_t)t * 8) = *reinterpret_cast<const uint4*>(v);
+        return;
+      }
+      t -= nchunk;
+    }
+  }
+}
+static int pack_weights(const fm_ppo_net* net, cudaStream_t s) {
+  if (!net->params_pk) return 0;
+  const int total = 2 * ((net->obs_pad >> 3) * 128 + 16 * 128) + 16 * (net->out_pad + 16);
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, s>>>(*net);
+  return 0;
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,9 +449,9 @@ int fm_policy_forward(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* o
                       void* act_env, float* act_raw, float* logp, float* value, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n > ws->cap || n % 64) { g_ppo_err = "fm_policy_forward: n must be a multiple of 64 and <= workspace capacity"; return 1; }
-  if (g_use_tc5) {
+  if (g_use_tc5 & 1) {
     // fused tcgen05 path: the three layers of a net in one kernel, hidden activations stay in shared memory / TMEM
-    const bf16* P = net->params_bf16; const float* Pf = net->params;
+    const bf16* P = net->params_pk; const float* Pf = net->params;
     int* status = reinterpret_cast<int*>(ws->scal + 8);
     if (int rc = fm_mlp_forward_tc5(obs, net->obs_dim, net->obs_dim, nullptr, P + net->w1[0], P + net->w2[0], P + net->w3[0], Pf + net->b1[0],
                                     Pf + net->b2[0], Pf + net->b3[0], ws->out[0], net->out_pad, nullptr, nullptr, n, net->obs_pad, status, stream)) { g_ppo_err = fm_tc5_last_error(); return rc; }
@@ -451,9 +490,21 @@ int fm_ppo_update(const fm_ppo_net* net, const fm_ppo_ws* ws, const float* obs, 
   cudaStream_t s = (cudaStream_t)stream;
   if (n > ws->cap || n % 64) { g_ppo_err = "fm_ppo_update: n must be a multiple of 64 and <= workspace capacity"; return 1; }
   size_t tot = (size_t)n * net->obs_pad;
-  cast_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(obs, n, net->obs_dim, ws->x, net->obs_pad, idx);
-  if (int rc = mlp_forward(net, ws, 0, n, s)) return rc;
-  if (int rc = mlp_forward(net, ws, 1, n, s)) return rc;
+  cast_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(obs, n, net->obs_dim, ws->x, net->obs_pad, idx);   // x in bf16: the dW1 operand
+  if (g_use_tc5 & 2) {
+    // the SAME fused tcgen05 forward as the rollout (gathers the minibatch rows itself, keeps h1 / h2 for the backward pass): the
+    // first epoch's probability ratio is exactly 1 and the forward is 2 launches instead of 6 (80 us per optimiser step less at
+    // 8192-row minibatches); fm_ppo_use_tcgen05(1) keeps the mma.sync chain here
+    const bf16* P = net->params_pk; const float* Pf = net->params;
+    int* status = reinterpret_cast<int*>(ws->scal + 8);
+    for (int which = 0; which < 2; ++which)
+      if (int rc = fm_mlp_forward_tc5(obs, net->obs_dim, net->obs_dim, idx, P + net->w1[which], P + net->w2[which], P + net->w3[which],
+                                      Pf + net->b1[which], Pf + net->b2[which], Pf + net->b3[which], ws->out[which], which == 0 ? net->out_pad : 16,
+                                      ws->h1[which], ws->h2[which], n, net->obs_pad, status, stream)) { g_ppo_err = fm_tc5_last_error(); return rc; }
+  } else {
+    if (int rc = mlp_forward(net, ws, 0, n, s)) return rc;
+    if (int rc = mlp_forward(net, ws, 1, n, s)) return rc;
+  }
   if (normalize_advantage) adv_stats_kernel<<<1, 256, 0, s>>>(adv, idx, n, ws->scal);
   ppo_loss_kernel<<<(n + 127) / 128, 128, 0, s>>>(ws->out[0], net->out_pad, ws->out[1], 16, net->params + net->log_std, actions, old_logp, adv, ret, idx,
                                                  n, net->act_dim, net->discrete, clip_range, vf_coef, ent_coef, normalize_advantage, ws->scal,
@@ -478,6 +529,7 @@ int fm_adam_step(const fm_ppo_net* net, float lr, float beta1, float beta2, floa
   adam_kernel<<<FM_ADAM_BLOCKS, 256, 0, s>>>(net->params, net->params_bf16, net->grads, net->adam_m, net->adam_v, net->n_params, lr, beta1, beta2, eps,
                                              max_grad_norm, grad_scale, step, norm2, stats);
   adam_count_kernel<<<1, 1, 0, s>>>(step, norm2, stats);
+  pack_weights(net, s);
   PPO_CUDA(cudaGetLastError());
   return 0;
 }
@@ -493,6 +545,7 @@ int fm_monitor_update(const uint8_t* terminated, const float* ep_info, int n, in
 }
 int fm_ppo_sync_bf16(const fm_ppo_net* net, void* stream) {
   f32_to_bf16_kernel<<<(net->n_params + 255) / 256, 256, 0, (cudaStream_t)stream>>>(net->params, net->params_bf16, net->n_params);
+  pack_weights(net, (cudaStream_t)stream);
   PPO_CUDA(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,8 @@ class fm_ppo_net(C.Structure):
                 ("n_params", C.c_int32), ("r0", C.c_int32), ("r1", C.c_int32),
                 ("w1", C.c_int32 * 2), ("b1", C.c_int32 * 2), ("w2", C.c_int32 * 2), ("b2", C.c_int32 * 2), ("w3", C.c_int32 * 2),
                 ("b3", C.c_int32 * 2), ("log_std", C.c_int32), ("r2", C.c_int32),
-                ("params", C.c_void_p), ("params_bf16", C.c_void_p), ("grads", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p)]
+                ("params", C.c_void_p), ("params_bf16", C.c_void_p), ("grads", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+                ("params_pk", C.c_void_p)]
 
 
 class fm_ppo_ws(C.Structure):
@@ -82,6 +83,7 @@ class PolicyValueNet:
         self.off, self.n_params = off, o
         self.params = torch.zeros(o, dtype=torch.float32, device=self.dev)
         self.params_bf16 = torch.zeros(o, dtype=torch.bfloat16, device=self.dev)
+        self.params_pk = torch.zeros(o, dtype=torch.bfloat16, device=self.dev)   # weights in the tcgen05 B-operand image (fm_ppo.cu pack_weights_kernel)
         self.grads = torch.zeros(o, dtype=torch.float32, device=self.dev)
         self.adam_m = torch.zeros(o, dtype=torch.float32, device=self.dev)
         self.adam_v = torch.zeros(o, dtype=torch.float32, device=self.dev)
@@ -90,7 +92,8 @@ class PolicyValueNet:
                               w2=(C.c_int32 * 2)(off[("w2", 0)], off[("w2", 1)]), b2=(C.c_int32 * 2)(off[("b2", 0)], off[("b2", 1)]),
                               w3=(C.c_int32 * 2)(off[("w3", 0)], off[("w3", 1)]), b3=(C.c_int32 * 2)(off[("b3", 0)], off[("b3", 1)]),
                               log_std=off["log_std"], params=self.params.data_ptr(), params_bf16=self.params_bf16.data_ptr(),
-                              grads=self.grads.data_ptr(), adam_m=self.adam_m.data_ptr(), adam_v=self.adam_v.data_ptr())
+                              grads=self.grads.data_ptr(), adam_m=self.adam_m.data_ptr(), adam_v=self.adam_v.data_ptr(),
+                              params_pk=self.params_pk.data_ptr())
         self._ws = None
         self._alloc_ws(capacity)
         self.launches = 0
@@ -373,7 +376,7 @@ class PPO:
                                        self.stats.data_ptr(), s))
 
     def _capture_graphs(self):
-        """One optimiser step = 33 short launches (launch-bound: K <= 320, N = 128 GEMMs): captured once into CUDA graphs and
+        """One optimiser step = 30 short launches (forward: the fused tcgen05 MLP per net; backward: K <= 384, N = 128 mma.sync GEMMs): captured once into CUDA graphs and
         replayed with a static minibatch-index buffer; Adam's step count lives on the device (stats[7]).  With several ranks the
         NCCL all-reduce stays between two graphs (update | all-reduce | Adam)."""
         pol = self.pol
@@ -421,7 +424,7 @@ class PPO:
                     idx = perm[b * self.batch_size:(b + 1) * self.batch_size].contiguous()
                     self._minibatch_eager(idx.data_ptr(), pol.adam_step)
                 n_updates += 1
-                self.launches += 33
+                self.launches += 30
         if self.use_graph and self._graphs is None:
             self._capture_graphs()
         return {"n_updates": n_updates, "policy_loss": float(self.stats[0]) / max(n_updates, 1), "value_loss": float(self.stats[1]) / max(n_updates, 1),

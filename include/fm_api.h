@@ -114,11 +114,12 @@ int fm_ppo_sync_bf16(const fm_ppo_net* net, void* stream);
  * ring f32[100,2] (return, length of the last 100 episodes over all envs), ring_head i32[1] = episodes so far. */
 int fm_monitor_update(const uint8_t* terminated, const float* ep_info, int n, int16_t* hist, int16_t* first, int32_t* count,
                       float* ring, int32_t* ring_head, void* stream);
-/* fused 3-layer MLP forward of one net on tcgen05 (TMEM accumulators); used by fm_policy_forward unless switched off */
+/* fused 3-layer MLP forward of one net on tcgen05 (TMEM accumulators); used by fm_policy_forward and fm_ppo_update unless switched
+ * off.  w1 / w2 / w3: bf16 weights in the B-operand image, 16-byte chunks [K / 8][N][8 consecutive k] (fm_ppo_net.params_pk). */
 int fm_mlp_forward_tc5(const float* x, int ld_x, int d_in, const int* idx, const void* w1, const void* w2, const void* w3,
                        const float* b1, const float* b2, const float* b3, float* out, int op, void* h1, void* h2, int n, int kp,
                        int* status, void* stream);
-void fm_ppo_use_tcgen05(int on);
+void fm_ppo_use_tcgen05(int on);   /* bit 0: rollout forward, bit 1: the update's forward (default 3 = both; 0 = mma.sync GEMM chain) */
 const char* fm_ppo_last_error(void);
 
 #ifdef __cplusplus

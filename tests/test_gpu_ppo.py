@@ -161,6 +161,27 @@ def test_ppo_learn_smoke_and_sb3_roundtrip(tmp_path):
         assert torch.equal(v, sd[k])
 
 
+def test_update_forward_on_tcgen05_is_equivalent_to_the_gemm_chain():
+    """default (fm_ppo_use_tcgen05(3)): the update's forward runs the fused tcgen05 kernel (row gather, h1 / h2 kept for the backward
+    pass); mode 1 keeps the mma.sync chain there; one PPO iteration from identical state must end at the same parameters up to bf16 noise"""
+    from factory_marl_b200.ppo import PPO
+    from factory_marl_b200.vec_env import FactoryVecEnv
+    res = []
+    for mode in (3, 1):
+        env = FactoryVecEnv("PauseIKToggleEnv", num_envs=128, num_arms=2, seeds=list(range(42, 170)))
+        algo = PPO(env, n_steps=4, batch_size=256, n_epochs=2, seed=1, use_graph=False)
+        algo.pol.lib.fm_ppo_use_tcgen05(mode)
+        try:
+            algo.collect_rollouts(); info = algo.train()
+        finally:
+            algo.pol.lib.fm_ppo_use_tcgen05(3)
+        algo.pol.check_status()
+        res.append((algo.pol.params.clone(), info))
+    d = (res[0][0] - res[1][0]).abs().max()
+    assert float(d) < 2e-3 and torch.isfinite(res[1][0]).all(), float(d)        # 4 Adam steps of lr 3e-4: identical signs almost everywhere
+    assert abs(res[0][1]["value_loss"] - res[1][1]["value_loss"]) < 2e-2 * max(1.0, abs(res[0][1]["value_loss"]))
+
+
 def test_ppo_learn_six_arms():
     """num_arms = 6: 274-dim observations, 48-dim Box actions through rollout (tcgen05 forward, N = 48) and update"""
     from factory_marl_b200.ppo import PPO
@@ -189,7 +210,7 @@ def test_tcgen05_mlp_matches_mma_sync_and_fp32(obs_dim, act_dim, discrete):
     pol.lib.fm_ppo_use_tcgen05(0)
     pol.forward(x, deterministic=True)
     out_mma = pol._bufs["out"][0][:640].clone(); val_mma = pol.value[:640].clone()
-    pol.lib.fm_ppo_use_tcgen05(1)
+    pol.lib.fm_ppo_use_tcgen05(3)
     pi, v = fwd(x)
     n_out = pi.shape[1]
     assert status == 0, "mbarrier wait timed out in the tcgen05 kernel"
