@@ -1519,10 +1519,13 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
           float u[3]; B.contact_u(c, B.a, u);
           const float mu = s.c_mu[c];
           unsigned bits = 0; float mx = 0.f;
+          const bool warm = s.c_f[c][0] > 0.f || s.c_f[c][1] > 0.f || s.c_f[c][2] > 0.f || s.c_f[c][3] > 0.f;   // matched by the warm-start key
           for (int r = 0; r < 4; ++r) {
             const int tq = 1 + (r >> 1); const float cf = (r & 1) ? -mu : mu;
             const float x = u[0] + cf * u[tq] - s.c_aref[c][r];
-            const bool on = x < 0.f;
+            // first pass: a row that carried force in the previous solve stays in the set.  At the warm start x = -f R, and R is
+            // 1e-6..1e-8: its sign is noise against the sub-step's change of aref, so the evaluated set would be half wrong
+            const bool on = (it == 0 && warm) ? s.c_f[c][r] > 0.f : x < 0.f;
             const int bit = 4 * item + r;
             if (on) bits |= 1u << (bit & 31);
             if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) mx = fmaxf(mx, fabsf(x));
@@ -1537,7 +1540,7 @@ FM_HD bool island_newton_warp(EnvS<NA>& s, const FmDevModel& m, int root, Lanes&
           const float* aa = B.a + B.off[ni];
           float x; bool on;
           if (code & 0x1000) { x = aa[7] - aa[8] - s.arow_aref[a][r]; on = true; }
-          else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; x = sg * aa[d] - s.arow_aref[a][r]; on = x < 0.f; }
+          else { const int d = code & 255; const float sg = (code >> 8) ? -1.f : 1.f; x = sg * aa[d] - s.arow_aref[a][r]; on = x < 0.f || (it == 0 && s.arow_f[a][r] > 0.f); }
           const int bit = 4 * nc + rr;
           if (on) FM_ATOMIC_OR(reinterpret_cast<int*>(&B.act[bit >> 5]), (int)(1u << (bit & 31)));
           if (on != (((B.prev[bit >> 5] >> (bit & 31)) & 1u) != 0u)) { float ax = fabsf(x); int mi; memcpy(&mi, &ax, 4); FM_ATOMIC_MAXI(B.chg, mi); }
