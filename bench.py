@@ -175,6 +175,7 @@ def time_env_steps(env, policy_fn, obs, K, flush, world, dist):
     if world > 1:
         dist.barrier()
     total = sum(a.elapsed_time(c) for a, b, c in ev)
+    time_env_steps.last_kernel_ms = [b.elapsed_time(c) for a, b, c in ev]       # per-launch spread (one launch per step)
     return total, sum(a.elapsed_time(b) for a, b, c in ev) / K, sum(b.elapsed_time(c) for a, b, c in ev) / K, obs
 
 
@@ -219,6 +220,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     step_ms, act_ms, kern_ms, obs = time_env_steps(env, pol.act, obs, K, flush, world, dist)
+    kern_each = list(time_env_steps.last_kernel_ms)
     sampler.stop_flag = True
     launches = env.gpu_launches + pol.launches - l0
     total_ms = fdist.max_over_ranks(step_ms, dev)
@@ -388,7 +390,8 @@ def run_ours(args):
                            "block_shape": "14 envs x 12 warps per block, one block per SM"},
                 "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
                              "traffic": dram_env * n if dram_env else None, "traffic_source": dram_src,
-                             "kernel": "fm_step_kernel", "kernel_ms": kern_ms, "act_ms": act_ms,
+                             "kernel": "fm_step_kernel", "kernel_ms": kern_ms, "kernel_ms_min": min(kern_each), "kernel_ms_max": max(kern_each),
+                             "kernel_ms_spread": (max(kern_each) - min(kern_each)) / (2.0 * kern_ms), "act_ms": act_ms,
                              "flop_per_env_step": FLOP_PER_ENV_STEP, "flop_per_env_step_executed": FLOP_PER_ENV_STEP_EXECUTED,
                              "achieved_executed": FLOP_PER_ENV_STEP_EXECUTED * n / (kern_ms * 1e-3) / 1e12,
                              "frac_executed": FLOP_PER_ENV_STEP_EXECUTED * n / (kern_ms * 1e-3) / 1e12 / fp32_peak,
