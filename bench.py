@@ -295,10 +295,13 @@ def run_ours(args):
         e1.record(); torch.cuda.synchronize()
         for name, t in outs[0].items():
             setattr(c, name, t)
-        return world * n * Ke / (fdist.max_over_ranks(e0.elapsed_time(e1), dev) * 1e-3)
+        return fdist.max_over_ranks(e0.elapsed_time(e1), dev)
 
-    e2e_sync = e2e_loop(False)
-    e2e_pipe = e2e_loop(True)
+    # the two variants run on consecutive windows of the same episode stream, whose cost drifts by several per cent from window
+    # to window: A B B A order, each variant's time summed over its two windows
+    t_sync, t_pipe = e2e_loop(False), e2e_loop(True)
+    t_pipe += e2e_loop(True); t_sync += e2e_loop(False)
+    e2e_sync, e2e_pipe = world * n * 2 * Ke / (t_sync * 1e-3), world * n * 2 * Ke / (t_pipe * 1e-3)
     e2e_value = max(e2e_sync, e2e_pipe)
     h2d = host_acts[0].numel() * 4
     d2h = host_obs[0].numel() * 4 + host_rew[0].numel() * 4 + host_done[0].numel()
