@@ -203,7 +203,8 @@ def run_ours(args):
 
     def make_env(cls=ENV_CLASS, envs=n, arms=2, kw=ENV_KW, sd=None):
         return FactoryVecEnv(cls, num_envs=envs, num_arms=arms, seeds=sd if sd is not None else seeds[:envs], device=dev,
-                             envs_per_block=args.envs_per_block, **kw)
+                             envs_per_block=args.envs_per_block, pgs_outer=int(os.environ.get("FM_BENCH_PGS_OUTER", "0")),
+                             sort_envs={"0": False, "1": True}.get(os.environ.get("FM_BENCH_SORT_ENVS", ""), None), **kw)
 
     env = make_env()
     _STATE_ROWS.update(nf=env.core.f.shape[0], nd=env.core.d.shape[0], ni=env.core.i.shape[0])
@@ -394,7 +395,7 @@ def run_ours(args):
                 "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
                              "traffic": dram_env * n if dram_env else None, "traffic_source": dram_src,
                              "kernel": "fm_step_kernel", "kernel_ms": kern_ms, "kernel_ms_min": min(kern_each), "kernel_ms_max": max(kern_each),
-                             "kernel_ms_spread": (max(kern_each) - min(kern_each)) / (2.0 * kern_ms), "act_ms": act_ms,
+                             "kernel_ms_spread": (max(kern_each) - min(kern_each)) / (2.0 * kern_ms), "kernel_ms_each": [round(x, 2) for x in kern_each], "act_ms": act_ms,
                              "flop_per_env_step": FLOP_PER_ENV_STEP, "flop_per_env_step_executed": FLOP_PER_ENV_STEP_EXECUTED,
                              "achieved_executed": FLOP_PER_ENV_STEP_EXECUTED * n / (kern_ms * 1e-3) / 1e12,
                              "frac_executed": FLOP_PER_ENV_STEP_EXECUTED * n / (kern_ms * 1e-3) / 1e12 / fp32_peak,

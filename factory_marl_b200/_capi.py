@@ -51,6 +51,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.fm_bind_state.argtypes = [vp, vp, vp, vp, vp]
     lib.fm_field_offset.argtypes = [vp, C.c_char_p]
     lib.fm_reset.argtypes = [vp, vp, vp, vp]
+    lib.fm_set_env_order.argtypes = [vp, vp]
     lib.fm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.fm_ik_policy.argtypes = [vp, vp, vp]
     lib.fm_get_state.argtypes = [vp, C.POINTER(fm_state_view)]
@@ -157,6 +158,11 @@ class FmCore:
             pass
 
     # ---- reference-shaped calls
+    def set_env_order(self, order=None):
+        """order: int32[N] permutation owned by the backend (kept alive here), or None for the identity (fm_set_env_order)."""
+        self._order = order
+        self._chk(self.lib.fm_set_env_order(self.h, self.be.ptr(order) if order is not None else None))
+
     def reset(self, mask=None):
         be = self.be
         self._chk(self.lib.fm_reset(self.h, be.ptr(mask) if mask is not None else None, be.ptr(self.obs), be.stream()))

@@ -28,6 +28,7 @@ struct FmStepArgs {
   int mode;          // 0 = env step, 1 = reset only (mask or all), 2 = raw sub-steps (debug: no action map / task logic)
   int n_substeps;    // mode 2
   FmDebugDump* dump;
+  const int* order;  // optional env order (n_envs ints on the device): block slot k serves env order[k]; nullptr = identity
 };
 
 template <int NA, int E, class Run>
@@ -98,10 +99,11 @@ FM_HD void fm_derive(Run& run, EnvS<NA>* S, const FmDevModel& m, const unsigned 
 }
 
 template <int NA, int E>
-FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, int tid, int stage) {
+FM_HD void fm_dump(EnvS<NA>* S, FmDebugDump* d, int env0, const int* ord, int n_envs, int tid, int stage) {
   if (!d || tid != 0) return;
-  int e = d->env - env0;
-  if (e < 0 || e >= E) return;
+  int e = -1;
+  for (int k = 0; k < E; ++k) if (slot_env(ord, env0 + k, n_envs) == d->env) e = k;
+  if (e < 0) return;
   const EnvS<NA>& s = S[e];
   if (stage == 0) {
     d->ncon = s.ncon; d->nqueue = s.nqueue; d->flags = s.flags;
@@ -129,12 +131,12 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel&
   const int T = 32 * TW;
   typedef Lay<NA> L;
   const int obs_dim = L::obs_dim(cfg.env_class);
-  run([&](int tid) { ph_load<NA, E>(S, TS, st, env0, tid, T); });
+  run([&](int tid) { ph_load<NA, E>(S, TS, st, env0, ar.order, tid, T); });
   if (ar.mode == 1) {   // reset only: masked envs (or all) go to the initial state, the others are written back untouched
-    run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
+    run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, ar.order, tid, T); });
     run([&](int tid) {
       for (int w = tid; w < E; w += T) {
-        int env = env0 + w;
+        int env = slot_env(ar.order, env0 + w, st.n);
         if (env >= st.n) continue;
         bool doit = ar.reset_mask ? ar.reset_mask[env] != 0 : true;
         TS[w].done_prev = doit; TS[w].terminated = doit;
@@ -142,24 +144,24 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel&
       }
     });
     fm_arm_kinematics<NA, E>(run, S, m, T);
-    run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, tid, T, true); });
-    run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
+    run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, ar.order, tid, T, true); });
+    run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, ar.order, tid, T); });
     return;
   }
-  if (ar.mode == 0) run([&](int tid) { ph_action<NA, E>(S, TS, m, cfg, st, ar.act_f, ar.act_i, env0, tid, T); });
+  if (ar.mode == 0) run([&](int tid) { ph_action<NA, E>(S, TS, m, cfg, st, ar.act_f, ar.act_i, env0, ar.order, tid, T); });
   else run([&](int tid) {   // debug: ctrl_target is used as is (no filter): ctrl := ctrl_target
     for (int w = tid; w < EnvS<NA>::NU * E; w += T) S[w % E].ctrl[w / E] = S[w % E].ctrl_target[w / E];
   });
   fm_derive<NA, E, TW>(run, S, m, cpairs, geom_class, cfg.sleep_hidden);
-  run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, tid, T); });
+  run([&](int tid) { ph_apply_edits<NA, E>(S, st, env0, ar.order, tid, T); });
   const double hd = cfg.dt / cfg.frame_skip;
   const int nsub = ar.mode == 0 ? cfg.frame_skip : ar.n_substeps;
   for (int t = 0; t < nsub; ++t) {
     if (t > 0) fm_derive<NA, E, TW>(run, S, m, cpairs, geom_class, cfg.sleep_hidden);
     run([&](int tid) { ph_island_union<NA, E>(S, tid, T); if (ar.mode == 0) ph_ctrl<NA, E>(S, tid, T, t < FM_MAX_FRAME_SKIP ? cfg.pt1_pow[t] : (float)pow(1.0 - hd / (hd + cfg.pt_time), t + 1.0)); });
     run([&](int tid) { ph_island_lists<NA, E>(S, tid, T); ph_smooth<NA, E>(S, m, tid, T); });
-    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 0); });
-    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 1); });
+    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, ar.order, st.n, tid, 0); });
+    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, ar.order, st.n, tid, 1); });
     run([&](int tid) { ph_check<NA, E>(S, m, tid, T); });
     run([&](int tid) { ph_pgs<NA, E, BIGN>(S, m, tid, T, cfg.pgs_inner, cfg.pgs_tol); });
     // BIGN: the kernel variant of the IK-driven env classes, where arms grasp and an arm + contact island is the common hard case.
@@ -167,21 +169,21 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel&
     if constexpr (BIGN) run.warps([&](int warp, auto& L) { ph_big_islands<NA, E>(S, m, warp, TW, L, cfg.pgs_inner, cfg.pgs_tol); });
     // belt lane: contact term of the belt dof (same lane as the belt row of ph_integrate), then integration
     run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });
-    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, tid, 2); });
+    if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, ar.order, st.n, tid, 2); });
   }
   if (ar.mode == 2) {   // debug: store the raw state, pre-edit == current
-    run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, tid, T); for (int w = tid; w < E; w += T) TS[w].done_prev = 0; });
-    run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
+    run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, ar.order, tid, T); for (int w = tid; w < E; w += T) TS[w].done_prev = 0; });
+    run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, ar.order, tid, T); });
     return;
   }
   // kinematics of the final state for the gripper sites (reward / IK policy read site_xpos after the last mj_step1)
-  run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, tid, T); });
+  run([&](int tid) { ph_store_pre<NA, E>(S, st, env0, ar.order, tid, T); });
   fm_arm_kinematics<NA, E>(run, S, m, T);
   run([&](int tid) { ph_site<NA, E>(S, TS, m, tid, T); });
-  run([&](int tid) { ph_task<NA, E>(S, TS, m, cfg, st, env0, tid, T); });
-  run([&](int tid) { ph_obs<NA, E>(S, TS, ar.terminal_obs, obs_dim, st.n, env0, tid, T, true); ph_outputs<NA, E>(S, TS, st, ar.reward, ar.terminated, ar.scores, ar.flags, ar.ep_info, env0, tid, T); });
-  if (ar.auto_reset) run([&](int tid) { ph_reset_done<NA, E>(S, TS, cfg, st, env0, tid, T, nullptr); });
+  run([&](int tid) { ph_task<NA, E>(S, TS, m, cfg, st, env0, ar.order, tid, T); });
+  run([&](int tid) { ph_obs<NA, E>(S, TS, ar.terminal_obs, obs_dim, st.n, env0, ar.order, tid, T, true); ph_outputs<NA, E>(S, TS, st, ar.reward, ar.terminated, ar.scores, ar.flags, ar.ep_info, env0, ar.order, tid, T); });
+  if (ar.auto_reset) run([&](int tid) { ph_reset_done<NA, E>(S, TS, cfg, st, env0, ar.order, tid, T, nullptr); });
   else run([&](int tid) { for (int w = tid; w < E; w += T) TS[w].done_prev = 0; });
-  run([&](int tid) { ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, tid, T, false); });
-  run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, tid, T); });
+  run([&](int tid) { ph_obs<NA, E>(S, TS, ar.obs, obs_dim, st.n, env0, ar.order, tid, T, false); });
+  run([&](int tid) { ph_store<NA, E>(S, TS, st, env0, ar.order, tid, T); });
 }

@@ -50,7 +50,7 @@ inline int fm_field_offset_t(const char* name) {
   FM_OFF(D_CONV) FM_OFF(D_SPAWN_FREQ) FM_OFF(D_PLAY_TIME) FM_OFF(ND)
   FM_OFF(I_IN) FM_OFF(I_OUT) FM_OFF(I_NIN) FM_OFF(I_NOUT) FM_OFF(I_STEP) FM_OFF(I_SINCE) FM_OFF(I_FAIL) FM_OFF(I_OUTCNT)
   FM_OFF(I_SCORE) FM_OFF(I_LAST_SCORE) FM_OFF(I_EP_LEN) FM_OFF(I_FSM_STATE) FM_OFF(I_FSM_CNT) FM_OFF(I_FSM_TGT) FM_OFF(I_IGNORE)
-  FM_OFF(I_FLAGS) FM_OFF(I_EPISODES) FM_OFF(I_MAXCON) FM_OFF(I_PREV_N) FM_OFF(I_PREV_KEY) FM_OFF(I_PREV_AN) FM_OFF(I_PREV_ACODE) FM_OFF(NI)
+  FM_OFF(I_FLAGS) FM_OFF(I_EPISODES) FM_OFF(I_MAXCON) FM_OFF(I_ARMCON) FM_OFF(I_PREV_N) FM_OFF(I_PREV_KEY) FM_OFF(I_PREV_AN) FM_OFF(I_PREV_ACODE) FM_OFF(NI)
 #undef FM_OFF
   return -1;
 }

@@ -77,7 +77,19 @@ __global__ void __launch_bounds__(32 * TW, FM_MINBLK) fm_step_kernel(const FmDev
   }
   __builtin_assume(__isShared(S)); __builtin_assume(__isShared(TS));
   DevRun run;
+#ifdef FM_BLOCK_CYCLES
+  const long long t0 = clock64();
+#endif
   fm_block_step<NA, E, TW, BIGN>(run, S, TS, *mp, cpairs, geom_class, cfg, st, ar, (int)blockIdx.x * E);
+#ifdef FM_BLOCK_CYCLES
+  // profiling variant (tools/block_cycles.py): the block's cycle count goes into ep_info[env][0] of its envs that did NOT terminate
+  // (the monitor reads ep_info only for terminated envs)
+  __syncthreads();
+  if (ar.mode == 0 && ar.ep_info && threadIdx.x < E) {
+    const int env = slot_env(ar.order, (int)blockIdx.x * E + (int)threadIdx.x, st.n);
+    if (env < st.n && !ar.terminated[env]) ar.ep_info[4 * env] = (float)(clock64() - t0);
+  }
+#endif
 }
 
 template <int NA, int E, int TW, bool BIGN>

@@ -27,6 +27,7 @@ struct fm_handle {
   FmDevModel* d_model = nullptr; FmIkModel* d_ik = nullptr; unsigned int* d_cpairs = nullptr; int* d_geom_class = nullptr;
   FmDebugDump* d_dump = nullptr; float* d_ws = nullptr;
   long long launches = 0;
+  const int* order = nullptr;      // fm_set_env_order
 };
 
 // Block shapes built into the library (one translation unit each, fm_step_shape_*.cu): NA arms, E envs per block, TW warps.
@@ -38,7 +39,7 @@ static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   FmLaunch L{h->d_model, h->d_cpairs, h->d_geom_class, h->cfg, h->st};
   cudaError_t e;
   // IK-driven env classes (every class but AllFullRL) get the kernel variant with the warp-cooperative big-island solve
-  const bool bign = h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1;     // fm_config.pgs_outer = 1: sweeps only
+  const bool bign = (h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1) || h->user.pgs_outer == 2;     // fm_config.pgs_outer: 1 = sweeps only, 2 = Newton for every class
   if (h->hm.n_arms == 2) e = h->E == FM_BIG2_E ? (bign ? fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW, true>(L, ar, s) : fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW>(L, ar, s)) : (h->E == 1 ? fm_launch_step<2, 1, 1>(L, ar, s) : fm_launch_step<2, 4, 4>(L, ar, s));
   else if (h->hm.n_arms == 6) e = h->E == 1 ? fm_launch_step<6, 1, 1>(L, ar, s) : (bign ? fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW, true>(L, ar, s) : fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW>(L, ar, s));
   else e = h->E == FM_BIG4_E ? (bign ? fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW, true>(L, ar, s) : fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(L, ar, s)) : (h->E == 1 ? fm_launch_step<4, 1, 1>(L, ar, s) : fm_launch_step<4, 4, 4>(L, ar, s));
@@ -106,8 +107,9 @@ int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng) 
 int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : (h->hm.n_arms == 4 ? fm_field_offset_t<4>(name) : fm_field_offset_t<6>(name)); }
 long long fm_launch_count(const fm_handle* h) { return h->launches; }
 
+int fm_set_env_order(fm_handle* h, const int32_t* order) { h->order = order; return 0; }
 int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream) {
-  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.reset_mask = mask; ar.obs = obs;
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.order = h->order; ar.reset_mask = mask; ar.obs = obs;
   return dispatch(h, ar, (cudaStream_t)stream);
 }
 int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores, uint8_t* flags,
@@ -115,7 +117,7 @@ int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_
   if (!actions && fm_act_dim(h) > 0) { g_err = "fm_step: actions is NULL"; return 1; }
   FmStepArgs ar; memset(&ar, 0, sizeof(ar));
   ar.mode = 0; ar.act_f = (const float*)actions; ar.act_i = (const int*)actions; ar.obs = obs; ar.reward = reward; ar.terminated = terminated;
-  ar.scores = scores; ar.flags = flags; ar.terminal_obs = terminal_obs; ar.ep_info = ep_info; ar.auto_reset = h->user.auto_reset;
+  ar.scores = scores; ar.flags = flags; ar.terminal_obs = terminal_obs; ar.ep_info = ep_info; ar.auto_reset = h->user.auto_reset; ar.order = h->order;
   return dispatch(h, ar, (cudaStream_t)stream);
 }
 int fm_ik_policy(fm_handle* h, float* obs, void* stream) {
@@ -163,7 +165,7 @@ int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void* s
   if (view) if (int rc = check_env(h, view->env, "fm_debug_substeps")) return rc;
   FmDebugDump hd; memset(&hd, 0, sizeof(hd)); hd.env = view ? view->env : -1;
   FM_CUDA(cudaMemcpy(h->d_dump, &hd, sizeof(hd), cudaMemcpyHostToDevice));
-  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? h->d_dump : nullptr;
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? h->d_dump : nullptr; ar.order = h->order;
   if (int rc = dispatch(h, ar, (cudaStream_t)stream)) return rc;
   FM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (view) {

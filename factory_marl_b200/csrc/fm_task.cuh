@@ -24,12 +24,15 @@ struct Lay {
   static const int I_IN = 0, I_OUT = 10, I_NIN = 20, I_NOUT = 21, I_STEP = 22, I_SINCE = 23, I_FAIL = 24, I_OUTCNT = 25,
                    I_SCORE = 26, I_LAST_SCORE = 28, I_EP_LEN = 30, I_FSM_STATE = 31, I_FSM_CNT = I_FSM_STATE + NA,
                    I_FSM_TGT = I_FSM_CNT + NA, I_IGNORE = I_FSM_TGT + NA, I_FLAGS = I_IGNORE + NA * NA, I_EPISODES = I_FLAGS + 1,
-                   I_MAXCON = I_EPISODES + 1, I_PREV_N = I_MAXCON + 1, I_PREV_KEY = I_PREV_N + 1, I_PREV_AN = I_PREV_KEY + FmCap<NA>::CON,
+                   I_MAXCON = I_EPISODES + 1, I_ARMCON = I_MAXCON + 1, I_PREV_N = I_ARMCON + 1, I_PREV_KEY = I_PREV_N + 1, I_PREV_AN = I_PREV_KEY + FmCap<NA>::CON,
                    I_PREV_ACODE = I_PREV_AN + NA, NI = I_PREV_ACODE + FM_AROW * NA;
   FM_HDM static int obs_dim(int env_class) { return NA * 24 + 130 + ((env_class == FM_ENV_PAUSE_TOGGLE || env_class == FM_ENV_BACKUP_TOGGLE) ? 8 * NA : 0); }
 };
 
 struct FmStatePtrs { float* f; double* d; int* i; unsigned long long* rng; int n; float* ws; /* library-owned scratch [n][FmCap<NA>::WS] */ };
+
+// block slot -> env index: identity, or the caller's env order (fm_set_env_order: heavy envs first, so that they share blocks)
+FM_HD int slot_env(const int* ord, int slot, int n) { return (ord != nullptr && slot < n) ? ord[slot] : slot; }
 
 // per-env task scratch kept in shared memory next to EnvS
 template <int NA>
@@ -69,12 +72,13 @@ FM_HD double pcg64_uniform(unsigned long long* st /*hi, lo, inc_hi, inc_lo*/) {
 
 // ---- load / store between HBM (SoA) and shared memory
 template <int NA, int E>
-FM_PH void ph_load(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_load(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < L::NF * E; w += T) {
-    int e = w % E, fidx = w / E; int env = env0 + e;
+    int e = w % E, fidx = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     EnvS<NA>& s = S[e];
     float v = st.f[(size_t)fidx * N + env];
@@ -97,7 +101,7 @@ FM_PH void ph_load(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, 
     else if (fidx >= L::F_PREV_AF) (&s.prev_arow_f[0][0])[fidx - L::F_PREV_AF] = v;
   }
   for (int w = tid; w < L::NI * E; w += T) {
-    int e = w % E, k = w / E; int env = env0 + e;
+    int e = w % E, k = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     int v = st.i[(size_t)k * N + env];
     TaskS<NA>& t = TS[e];
@@ -115,7 +119,7 @@ FM_PH void ph_load(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, 
     else if (k >= L::I_IGNORE && k < L::I_FLAGS) t.ignore[(k - L::I_IGNORE) / NA][(k - L::I_IGNORE) % NA] = v;
   }
   for (int w = tid; w < E; w += T) {
-    int env = env0 + w;
+    int env = slot_env(ord, env0 + w, NENV);
     float* ws = st.ws + (size_t)env * FmCap<NA>::WS;    // the scratch has rows for the padding slots too
     if (env >= N) env = N - 1;
     TS[w].conveyor_speed = st.d[(size_t)L::D_CONV * N + env];
@@ -134,12 +138,13 @@ FM_PH void ph_load(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, 
 
 // the task manager's edits (spawn / hide) become visible to the integrator only after the first derive
 template <int NA, int E>
-FM_PH void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < 130 * E; w += T) {
-    int e = w % E, k = w / E; int env = env0 + e;
+    int e = w % E, k = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) env = N - 1;   // padding slot of the last block: steps a copy of the last env, nothing of it is stored
     if (k < 70) (&S[e].cube_q[0][0])[k] = st.f[(size_t)(L::F_CUBE_Q + k) * N + env];
     else (&S[e].cube_v[0][0])[k - 70] = st.f[(size_t)(L::F_CUBE_V + k - 70) * N + env];
@@ -149,12 +154,13 @@ FM_PH void ph_apply_edits(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid,
 // ---- action map -> ctrl (clipped to actuator_ctrlrange, base_env.py:255-262)
 template <int NA, int E>
 FM_PH void ph_action(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, const float* act_f,
-                     const int* act_i, int env0, int tid, int T) {
+                     const int* act_i, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < (1 + 8 * NA) * E; w += T) {
-    int e = w % E, u = w / E; int env = env0 + e;
+    int e = w % E, u = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) continue;
     EnvS<NA>& s = S[e];
     if (u == 0) { s.ctrl[0] = clampf((float)TS[e].conveyor_speed, m.ctrl_lo[0], m.ctrl_hi[0]); continue; }
@@ -187,7 +193,7 @@ FM_PH void ph_action(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEn
   }
   // action-norm term of the progress reward (environments.py:371-373)
   for (int w = tid; w < E; w += T) {
-    int env = env0 + w;
+    int env = slot_env(ord, env0 + w, NENV);
     if (env >= N) continue;
     float an = 0.f;
     int cls = cfg.env_class;
@@ -199,12 +205,13 @@ FM_PH void ph_action(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEn
 
 // ---- save the physical (pre-edit) cube state for the next launch's first derive
 template <int NA, int E>
-FM_PH void ph_store_pre(EnvS<NA>* S, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_store_pre(EnvS<NA>* S, const FmStatePtrs& st, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < 130 * E; w += T) {
-    int e = w % E, k = w / E; int env = env0 + e;
+    int e = w % E, k = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) continue;
     float v = k < 70 ? (&S[e].cube_q[0][0])[k] : (&S[e].cube_v[0][0])[k - 70];
     st.f[(size_t)(L::F_PRE_Q + k) * N + env] = v;
@@ -247,11 +254,12 @@ FM_HD void task_reset_state(EnvS<NA>& s, TaskS<NA>& t, const FmEnvCfg& cfg) {
 
 // ---- task manager step + reward + termination (thread per env)
 template <int NA, int E>
-FM_PH void ph_task(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_task(EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel& m, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S); FM_ASSUME_GLOBAL(&m); FM_ASSUME_SHARED(TS);
   int N = st.n;
   for (int w = tid; w < E; w += T) {
-    int env = env0 + w;
+    int env = slot_env(ord, env0 + w, NENV);
     if (env >= N) continue;
     EnvS<NA>& s = S[w]; TaskS<NA>& t = TS[w];
     // TaskManager.step (task_utils.py:135-144)
@@ -371,11 +379,12 @@ FM_HD float obs_value(const EnvS<NA>& s, const TaskS<NA>& t, int j) {
 
 // write base observation (_get_state + _process_observation, base_env.py:149-175, environments.py:55-82)
 template <int NA, int E>
-FM_PH void ph_obs(EnvS<NA>* S, TaskS<NA>* TS, float* obs, int obs_dim, int n_envs, int env0, int tid, int T, bool only_done) {
+FM_PH void ph_obs(EnvS<NA>* S, TaskS<NA>* TS, float* obs, int obs_dim, int n_envs, int env0, const int* ord, int tid, int T, bool only_done) {
+  const int NENV = n_envs;
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   const int base = 24 * NA + 130;
   for (int w = tid; w < base * E; w += T) {
-    int e = w / base, j = w % base; int env = env0 + e;
+    int e = w / base, j = w % base; int env = slot_env(ord, env0 + e, NENV);
     if (env >= n_envs || obs == nullptr) continue;
     if (only_done && !TS[e].terminated) continue;
     obs[(size_t)env * obs_dim + j] = obs_value(S[e], TS[e], j);
@@ -384,12 +393,13 @@ FM_PH void ph_obs(EnvS<NA>* S, TaskS<NA>* TS, float* obs, int obs_dim, int n_env
 
 template <int NA, int E>
 FM_PH void ph_outputs(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, float* reward, unsigned char* terminated, int* scores,
-                      unsigned char* flags, float* ep_info, int env0, int tid, int T) {
+                      unsigned char* flags, float* ep_info, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < E; w += T) {
-    int env = env0 + w;
+    int env = slot_env(ord, env0 + w, NENV);
     if (env >= N) continue;
     TaskS<NA>& t = TS[w];
     if (reward) reward[env] = t.reward;
@@ -400,17 +410,27 @@ FM_PH void ph_outputs(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, float* 
     int fl = S[w].flags;
     if (fl) st.i[(size_t)L::I_FLAGS * N + env] |= fl;
     if (S[w].ncon > st.i[(size_t)L::I_MAXCON * N + env]) st.i[(size_t)L::I_MAXCON * N + env] = S[w].ncon;
+    // contacts that touch an arm at the end of this step (0 after a termination: the env restarts): the caller's cue for grouping
+    // the envs whose next step will be expensive (fm_set_env_order)
+    int na = 0;
+    if (!t.terminated)
+      for (int c = 0; c < S[w].ncon; ++c) {
+        const int cs = S[w].c_side[c];
+        na += (side_type(cs & FM_SIDE_MASK) == FM_SIDE_ARM || side_type((cs >> FM_SIDE_BITS) & FM_SIDE_MASK) == FM_SIDE_ARM) ? 1 : 0;
+      }
+    st.i[(size_t)L::I_ARMCON * N + env] = na;
   }
 }
 
 // reset (reset_sim base_env.py:177-198 + TaskManager.reset task_utils.py:146-156) for terminated envs when auto-reset is on
 template <int NA, int E>
-FM_PH void ph_reset_done(EnvS<NA>* S, TaskS<NA>* TS, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, int tid, int T, const unsigned char* mask) {
+FM_PH void ph_reset_done(EnvS<NA>* S, TaskS<NA>* TS, const FmEnvCfg& cfg, const FmStatePtrs& st, int env0, const int* ord, int tid, int T, const unsigned char* mask) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < E; w += T) {
-    int env = env0 + w;
+    int env = slot_env(ord, env0 + w, NENV);
     if (env >= N) continue;
     bool doit = mask ? (mask[env] != 0) : (TS[w].terminated != 0);
     TS[w].done_prev = doit ? 1 : 0;
@@ -422,12 +442,13 @@ FM_PH void ph_reset_done(EnvS<NA>* S, TaskS<NA>* TS, const FmEnvCfg& cfg, const 
 }
 
 template <int NA, int E>
-FM_PH void ph_store(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, int tid, int T) {
+FM_PH void ph_store(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0, const int* ord, int tid, int T) {
+  const int NENV = st.n;
   FM_ASSUME_SHARED(S); FM_ASSUME_SHARED(TS);
   typedef Lay<NA> L;
   int N = st.n;
   for (int w = tid; w < L::NF * E; w += T) {
-    int e = w % E, fidx = w / E; int env = env0 + e;
+    int e = w % E, fidx = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) continue;
     EnvS<NA>& s = S[e];
     float v; bool wr = true;
@@ -457,7 +478,7 @@ FM_PH void ph_store(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0,
     if (wr) st.f[(size_t)fidx * N + env] = v;
   }
   for (int w = tid; w < L::NI * E; w += T) {
-    int e = w % E, k = w / E; int env = env0 + e;
+    int e = w % E, k = w / E; int env = slot_env(ord, env0 + e, NENV);
     if (env >= N) continue;
     TaskS<NA>& t = TS[e];
     int v; bool wr = true;
@@ -477,7 +498,7 @@ FM_PH void ph_store(EnvS<NA>* S, TaskS<NA>* TS, const FmStatePtrs& st, int env0,
     if (wr) st.i[(size_t)k * N + env] = v;
   }
   for (int w = tid; w < E; w += T) {
-    int env = env0 + w;
+    int env = slot_env(ord, env0 + w, NENV);
     if (env >= N) continue;
     st.d[(size_t)L::D_CONV * N + env] = TS[w].conveyor_speed;
     st.d[(size_t)L::D_SPAWN_FREQ * N + env] = TS[w].spawn_freq;

@@ -162,7 +162,7 @@ class FactoryVecEnv:
     (base_env.py:15-35) plus the ProgressRewardEnv weights (environments.py:252-259)."""
 
     def __init__(self, env_class: str = "PauseIKToggleEnv", num_envs: int = 8, num_arms: int = 2, seed=42, seeds=None,
-                 device="cuda:0", auto_reset: bool = True, max_num_objects: int = 10, render_mode=None, **env_kwargs):
+                 device="cuda:0", auto_reset: bool = True, max_num_objects: int = 10, render_mode=None, sort_envs=None, **env_kwargs):
         if not torch.cuda.is_available():
             raise RuntimeError("FactoryVecEnv needs a CUDA device (B200); there is no CPU path")
         if max_num_objects != 10:
@@ -183,6 +183,9 @@ class FactoryVecEnv:
         self.monitor = EpisodeMonitor(num_envs, self.device)
         self._actions = None
         self._step_id = 0
+        # order the envs by expected cost before every launch (fm_set_env_order); default: from the one-block-per-SM batch size
+        self.sort_envs = (num_envs >= 2048) if sort_envs is None else bool(sort_envs)
+        self._armcon_row, self._ncon_row, self._nin_row = self.core.off("I_ARMCON"), self.core.off("I_PREV_N"), self.core.off("I_NIN")
 
     # ---- VecEnv API
     def reset(self):
@@ -202,6 +205,12 @@ class FactoryVecEnv:
         c.env_step(self._actions)
         self._step_id += 1
         self.monitor.update(c.terminated, c.ep_info)
+        if self.sort_envs:
+            # a block lasts as long as its most expensive env and the launch as long as the slowest SM's two blocks: order the envs by
+            # expected cost (arm in contact, cubes in the scene, contacts), most expensive first, so that like envs share a block and
+            # the long blocks start first (measured + 9 % env-steps/s at 4096 envs; results do not depend on the order)
+            key = c.i[self._armcon_row] * 4096 + c.i[self._nin_row] * 64 + c.i[self._ncon_row]
+            c.set_env_order(torch.argsort(key, descending=True, stable=True).to(torch.int32))
         return c.obs, c.reward, c.terminated.bool(), (LazyInfos(self) if with_infos else None)
 
     def step(self, actions, with_infos: bool = True):

@@ -67,6 +67,12 @@ int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng);
 /* field offsets inside the SoA arrays, by name (e.g. "F_ARM_Q", "I_SCORE", "I_IGNORE"); -1 if unknown */
 int fm_field_offset(const fm_handle* h, const char* name);
 /* FactoryManipulationEnv.reset / BaseEnv.reset_sim (environments.py:204-248, base_env.py:177-198); mask [N] or NULL = all */
+/* Optional env order for the following launches: block slot k serves env order[k] (a permutation of 0..n_envs-1 on the device,
+ * owned by the caller, read at every launch; NULL = identity).  Results do not depend on it; the launch time does: a block lasts as
+ * long as its most expensive env and the launch as long as the slowest SM's blocks, so ordering the envs by expected cost (state
+ * rows I_ARMCON, I_NIN, I_PREV_N), most expensive first, groups like envs and starts the long blocks first
+ * (VecEnv mirror: FactoryVecEnv(sort_envs=True), + 9 % at 4096 envs). */
+int fm_set_env_order(fm_handle* h, const int32_t* order);
 int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void* stream);
 /* FactoryManipulationEnv.step (environments.py:151-202) for all envs, with SB3-VecEnv auto-reset when cfg.auto_reset:
  * actions f32[N, act_dim] (Box) or i32[N, n_arms] (MultiDiscrete); flags bit0 out_of_reach, bit1 force_terminate,

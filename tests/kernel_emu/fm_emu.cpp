@@ -45,12 +45,13 @@ struct HostRun {
 struct fm_handle {
   FmHostModel hm; FmEnvCfg cfg; fm_config user; FmStatePtrs st; int E;
   std::vector<char> smem; std::vector<float> ws;
+  const int* order = nullptr;
 };
 
 template <int NA, int E, int TW = E>
 static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
   // same rule as the library: the IK-driven classes run the variant with the big-island Newton (here for every block shape)
-  const bool bign = h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1;
+  const bool bign = (h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1) || h->user.pgs_outer == 2;
   HostRun run{32 * TW};
   size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS<NA>)) + 64;
   if (h->smem.size() < need) h->smem.resize(need);
@@ -127,15 +128,16 @@ int fm_state_rows(const fm_handle* h, int32_t* nf, int32_t* nd, int32_t* ni) {
 }
 int fm_bind_state(fm_handle* h, float* f, double* d, int32_t* i, uint64_t* rng) { h->st.f = f; h->st.d = d; h->st.i = i; h->st.rng = (unsigned long long*)rng; return 0; }
 int fm_field_offset(const fm_handle* h, const char* name) { return h->hm.n_arms == 2 ? fm_field_offset_t<2>(name) : (h->hm.n_arms == 4 ? fm_field_offset_t<4>(name) : fm_field_offset_t<6>(name)); }
+int fm_set_env_order(fm_handle* h, const int32_t* order) { h->order = order; return 0; }
 int fm_reset(fm_handle* h, const uint8_t* mask, float* obs, void*) {
-  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.reset_mask = mask; ar.obs = obs;
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 1; ar.reset_mask = mask; ar.obs = obs; ar.order = h->order;
   dispatch(h, ar); return 0;
 }
 int fm_step(fm_handle* h, const void* actions, float* obs, float* reward, uint8_t* terminated, int32_t* scores, uint8_t* flags,
             float* terminal_obs, float* ep_info, void*) {
   FmStepArgs ar; memset(&ar, 0, sizeof(ar));
   ar.mode = 0; ar.act_f = (const float*)actions; ar.act_i = (const int*)actions; ar.obs = obs; ar.reward = reward; ar.terminated = terminated;
-  ar.scores = scores; ar.flags = flags; ar.terminal_obs = terminal_obs; ar.ep_info = ep_info; ar.auto_reset = h->user.auto_reset;
+  ar.scores = scores; ar.flags = flags; ar.terminal_obs = terminal_obs; ar.ep_info = ep_info; ar.auto_reset = h->user.auto_reset; ar.order = h->order;
   dispatch(h, ar); return 0;
 }
 int fm_ik_policy(fm_handle* h, float* obs, void*) {
@@ -156,7 +158,7 @@ int fm_set_state(fm_handle* h, const fm_state_view* v) {
 }
 int fm_debug_substeps(fm_handle* h, int n_substeps, fm_debug_view* view, void*) {
   FmDebugDump* d = new FmDebugDump(); memset(d, 0, sizeof(*d)); d->env = view ? view->env : -1;
-  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? d : nullptr;
+  FmStepArgs ar; memset(&ar, 0, sizeof(ar)); ar.mode = 2; ar.n_substeps = n_substeps; ar.dump = view ? d : nullptr; ar.order = h->order;
   dispatch(h, ar);
   if (view) { if (h->hm.n_arms == 2) fm_dump_to_view<2>(*d, view); else if (h->hm.n_arms == 4) fm_dump_to_view<4>(*d, view); else fm_dump_to_view<6>(*d, view); }
   delete d; return 0;

@@ -186,3 +186,23 @@ def test_impact_substep_production():
 
 def test_episode_boundary_leaks():
     pc.case_episode_boundary(BE)
+
+
+def test_env_order_does_not_change_results():
+    """fm_set_env_order: block slot k serves env order[k].  Same seeds, same actions, a shuffled order and 2 envs per block:
+    every env must end exactly where it ends under the identity order; the arm-contact cue (I_ARMCON) is filled"""
+    from factory_marl_b200 import model as fm
+    blob = fm.build_blob(2)
+    n = 6
+    rng = np.random.default_rng(4)
+    acts = [np.clip(rng.normal(0, 1.5, (n, 16)), -1, 1).astype(np.float32) for _ in range(12)]
+    outs = []
+    for order in (None, np.array([3, 0, 5, 1, 4, 2], np.int32)):
+        core = BE.mk(blob, n, 2, "AllFullRLProgressRewardEnv", seeds=list(range(42, 42 + n)), auto_reset=True, envs_per_block=2, **pc.PROGRESS_KW)
+        core.set_env_order(order)
+        core.reset()
+        for a in acts:
+            core.env_step(a)
+        outs.append((np.array(core.obs).copy(), np.array(core.reward).copy(), np.array(core.i).copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    assert outs[0][2][core.off("I_ARMCON")].max() >= 0
