@@ -38,8 +38,10 @@ static int dispatch(fm_handle* h, const FmStepArgs& ar, cudaStream_t s) {
   if (!h->st.f) { g_err = "fm_bind_state was not called"; return 1; }
   FmLaunch L{h->d_model, h->d_cpairs, h->d_geom_class, h->cfg, h->st};
   cudaError_t e;
-  // IK-driven env classes (every class but AllFullRL) get the kernel variant with the warp-cooperative big-island solve
-  const bool bign = (h->cfg.env_class != FM_ENV_ALL_FULL && h->user.pgs_outer != 1) || h->user.pgs_outer == 2;     // fm_config.pgs_outer: 1 = sweeps only, 2 = Newton for every class
+  // the kernel variant with the warp-cooperative exact solve of arm + contact islands; fm_config.pgs_outer = 1: Gauss-Seidel sweeps only
+  // (the variant without that phase: 10 % faster per sub-step, but an arm collision then costs 32 one-lane sweeps per sub-step
+  // that do not converge, and its block sets the launch time)
+  const bool bign = h->user.pgs_outer != 1;
   if (h->hm.n_arms == 2) e = h->E == FM_BIG2_E ? (bign ? fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW, true>(L, ar, s) : fm_launch_step<2, FM_BIG2_E, FM_BIG2_TW>(L, ar, s)) : (h->E == 1 ? fm_launch_step<2, 1, 1>(L, ar, s) : fm_launch_step<2, 4, 4>(L, ar, s));
   else if (h->hm.n_arms == 6) e = h->E == 1 ? fm_launch_step<6, 1, 1>(L, ar, s) : (bign ? fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW, true>(L, ar, s) : fm_launch_step<6, FM_BIG6_E, FM_BIG6_TW>(L, ar, s));
   else e = h->E == FM_BIG4_E ? (bign ? fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW, true>(L, ar, s) : fm_launch_step<4, FM_BIG4_E, FM_BIG4_TW>(L, ar, s)) : (h->E == 1 ? fm_launch_step<4, 1, 1>(L, ar, s) : fm_launch_step<4, 4, 4>(L, ar, s));

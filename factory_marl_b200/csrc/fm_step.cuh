@@ -1310,7 +1310,10 @@ FM_HD void island_pgs_sweeps(EnvS<NA>& s, const FmDevModel& m, int node, int c0,
   // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
   // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236);
   // a lone arm with only its plate equality row is solved exactly by one visit
-  const int cap = (has_arm && c1 > c0) ? 8 * inner : ((c1 == c0 && single_row) ? 1 : inner);
+#ifndef FM_ARM_SWEEP_FACTOR
+#define FM_ARM_SWEEP_FACTOR 8
+#endif
+  const int cap = (has_arm && c1 > c0) ? FM_ARM_SWEEP_FACTOR * inner : ((c1 == c0 && single_row) ? 1 : inner);
   for (int it = 0; it < cap; ++it) {
     float maxd = 0.f;
     FM_DBG(fm_dbg_sweeps++; fm_dbg_visits += c1 - c0;)

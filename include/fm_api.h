@@ -26,7 +26,7 @@ enum { FM_FACTORY_MANIPULATION_ENV = 0, FM_SINGLE_FULL_RL = 1, FM_SINGLE_DELTA =
 typedef struct fm_config {
   int32_t n_envs, n_arms, env_class, auto_reset;
   /* pgs_inner: sweep cap of the PGS islands (0 = 4), pgs_tol: stopping criterion in m/s^2 (0 = 1e-3), pgs_outer: 1 = solve arm + contact
-   * islands by Gauss-Seidel sweeps only (0 = the IK-driven classes use the warp-cooperative active-set Newton).
+   * islands by Gauss-Seidel sweeps only (0 = the warp-cooperative active-set Newton, exact).
    * envs_per_block: block shape of the step kernel: 0 = by batch size, 1 | 4 = small batches / tests, 14 (two arms) | 7 (four
    * arms) | 6 (six arms; also stands in for 4 there) = one block per SM (default from 2048 envs).  reserved: 1 = keep hidden cubes live (strict mode), 0 = sleep them. */
   int32_t pgs_outer, pgs_inner, envs_per_block, reserved;
