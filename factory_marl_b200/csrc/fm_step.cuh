@@ -1096,7 +1096,9 @@ FM_PH void ph_smooth(EnvS<NA>* S, const FmDevModel& m, int tid, int T) {
 template <int NA> FM_HD float& c_res(EnvS<NA>& s, int c) { return reinterpret_cast<float*>(&s.raw_key[0])[c]; }
 template <int NA> FM_HD float& c_belt(EnvS<NA>& s, int c) { return reinterpret_cast<float*>(&s.raw_g[0])[c]; }
 template <int NA>
-FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool commit) {
+// out of line (like arm_rows_visit, island_pgs_sweeps, island_newton_warp): one copy for the check and the sweeps, and its registers
+// stay out of the fused loop's allocation — + 8 % env-steps/s for the four together (profiles/r2_ab/r4fgh_outline.log)
+FM_HDN float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool commit) {
   int cs = s.c_side[c];
   f3 p = ld3(s.c_p[c]), n = ld3(s.c_n[c]), t1 = ld3(s.c_t1[c]); f3 t2 = cross3(n, t1);
   SideW A, B;
@@ -1143,7 +1145,7 @@ FM_HD float contact_visit(EnvS<NA>& s, const FmDevModel& m, int c, bool commit) 
 
 // arm-local rows of arm a: mode 1 = Gauss-Seidel sweep, mode 2 = evaluate only (convergence check)
 template <int NA>
-FM_HD float arm_rows_visit(EnvS<NA>& s, int a, int mode) {
+FM_HDN float arm_rows_visit(EnvS<NA>& s, int a, int mode) {
   float* acc = &s.acc[61 + 9 * a];
   float maxd = 0.f;
   const float* Mi = s.Minv[a];
@@ -1306,7 +1308,8 @@ FM_HD bool island_newton_cube(EnvS<NA>& s, const FmDevModel& m, int k, int c0, i
 
 // Gauss-Seidel sweeps over one island (exact GS inside the island), starting from the warm start
 template <int NA>
-FM_HD void island_pgs_sweeps(EnvS<NA>& s, const FmDevModel& m, int node, int c0, int c1, bool has_arm, bool single_row, int inner, float tol) {
+// out of line like island_newton_warp: rarely taken, and its registers stay out of the fused loop's allocation (+ 4 %)
+FM_HDN void island_pgs_sweeps(EnvS<NA>& s, const FmDevModel& m, int node, int c0, int c1, bool has_arm, bool single_row, int inner, float tol) {
   // islands that contain an arm AND contacts (grasps, crashes) are stiff and strongly coupled through the 9x9 arm inertia:
   // they get 8x the sweep budget (spurious force peaks would otherwise trip the 200 N termination, base_env.py:226-236);
   // a lone arm with only its plate equality row is solved exactly by one visit
