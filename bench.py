@@ -48,8 +48,10 @@ def peaks():
 
 def ncu_dram_bytes_per_env():
     """dram__bytes_read.sum + dram__bytes_write.sum of fm_step_kernel per env-step from the committed `ncu --set full` capture of
-    this round (profiles/r2_step_kernel_dram.json, written by tools/ncu_segments.py --dram), else None"""
-    p = os.path.join(ROOT, "profiles", "r2_step_kernel_dram.json")
+    this round (profiles/r4k_step_kernel_dram.json: the end-state kernel; r2_step_kernel_dram.json: mid-round), else None"""
+    p = os.path.join(ROOT, "profiles", "r4k_step_kernel_dram.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r2_step_kernel_dram.json")
     if os.path.exists(p):
         d = json.load(open(p))
         return d["dram_bytes_per_launch"] / d["envs_per_launch"], d.get("source")
