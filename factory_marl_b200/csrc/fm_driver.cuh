@@ -164,8 +164,8 @@ FM_HD void fm_block_step(Run& run, EnvS<NA>* S, TaskS<NA>* TS, const FmDevModel&
     if (t == 0 && ar.dump) run([&](int tid) { fm_dump<NA, E>(S, ar.dump, env0, ar.order, st.n, tid, 1); });
     run([&](int tid) { ph_check<NA, E>(S, m, tid, T); });
     run([&](int tid) { ph_pgs<NA, E, BIGN>(S, m, tid, T, cfg.pgs_inner, cfg.pgs_tol); });
-    // BIGN: the kernel variant of the IK-driven env classes, where arms grasp and an arm + contact island is the common hard case.
-    // Compiled separately: the mere presence of this phase in the fused loop costs the other classes 19 % (profiles/README r2i)
+    // BIGN: the kernel variant with the exact warp solve of arm + contact islands (the default; fm_config.pgs_outer = 1 selects the
+    // other one).  Compiled separately: the presence of this phase in the fused loop costs the other phases ~10 % (profiles/README)
     if constexpr (BIGN) run.warps([&](int warp, auto& L) { ph_big_islands<NA, E>(S, m, warp, TW, L, cfg.pgs_inner, cfg.pgs_tol); });
     // belt lane: contact term of the belt dof (same lane as the belt row of ph_integrate), then integration
     run([&](int tid) { ph_belt<NA, E>(S, m, tid, T); if (t == nsub - 1) ph_force_check<NA, E>(S, tid, T); ph_integrate<NA, E>(S, m, tid, T); ph_save_forces<NA, E>(S, tid, T); });

@@ -50,7 +50,7 @@ struct fm_handle {
 
 template <int NA, int E, int TW = E>
 static void run_blocks(fm_handle* h, const FmStepArgs& ar) {
-  // same rule as the library: the IK-driven classes run the variant with the big-island Newton (here for every block shape)
+  // same rule as the library: the variant with the big-island Newton unless pgs_outer = 1 (here for every block shape)
   const bool bign = h->user.pgs_outer != 1;
   HostRun run{32 * TW};
   size_t need = E * (sizeof(EnvS<NA>) + sizeof(TaskS<NA>)) + 64;
