@@ -186,6 +186,7 @@ class FactoryVecEnv:
         # order the envs by expected cost before every launch (fm_set_env_order); default: from the one-block-per-SM batch size
         self.sort_envs = (num_envs >= 2048) if sort_envs is None else bool(sort_envs)
         self._armcon_row, self._ncon_row, self._nin_row = self.core.off("I_ARMCON"), self.core.off("I_PREV_N"), self.core.off("I_NIN")
+        self._since_row = self.core.off("I_SINCE")
 
     # ---- VecEnv API
     def reset(self):
@@ -209,7 +210,7 @@ class FactoryVecEnv:
             # a block lasts as long as its most expensive env and the launch as long as the slowest SM's two blocks: order the envs by
             # expected cost (arm in contact, cubes in the scene, contacts), most expensive first, so that like envs share a block and
             # the long blocks start first (measured + 9 % env-steps/s at 4096 envs; results do not depend on the order)
-            key = c.i[self._armcon_row] * 4096 + c.i[self._nin_row] * 64 + c.i[self._ncon_row]
+            key = c.i[self._armcon_row] * 4096 + c.i[self._nin_row] * 64 + c.i[self._ncon_row] + (c.i[self._since_row] < 8).int() * 48   # + a cube in flight
             c.set_env_order(torch.argsort(key, descending=True, stable=True).to(torch.int32))
         return c.obs, c.reward, c.terminated.bool(), (LazyInfos(self) if with_infos else None)
 
