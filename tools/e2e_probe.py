@@ -10,8 +10,11 @@ env.reset()
 rng = np.random.default_rng(0)
 Ke = 12
 host_acts = [torch.from_numpy(np.clip(rng.normal(0, 1, (n, 16)), -1, 1).astype(np.float32)).pin_memory() for _ in range(Ke)]
-for k in range(30):
+for k in range(230):                     # de-synchronise like bench.py: staggered resets over the first 200 steps
     env.step(host_acts[k % Ke].to(dev), with_infos=False)
+    if k < 200:
+        mask = torch.zeros(n, dtype=torch.uint8, device=dev); mask[k::200] = 1
+        env.core.reset(mask)
 torch.cuda.synchronize()
 c = env.core
 D = c.obs_dim
@@ -59,5 +62,5 @@ def loop(mode):
     if copies: print("   copy k finishes this long after kernel k ended (ms):", " ".join("%.2f" % r.elapsed_time(d) for k, r, d in copies))
     print("%-6s wall %.2f ms/step; kernel-span per step: %s" % (mode, (t1 - t0) * 1e3 / Ke, " ".join("%.1f" % x for x in ks)))
 
-for mode in ("sync", "pipe", "nosync", "sync", "pipe"):
+for mode in ("sync", "pipe", "pipe", "sync", "sync", "pipe", "pipe", "sync"):
     loop(mode)
