@@ -7,7 +7,8 @@ from factory_marl_b200.vec_env import FactoryVecEnv
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2072
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 112
 arms = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-env = FactoryVecEnv("PauseIKToggleEnv", num_envs=n, num_arms=arms, seeds=list(range(42, 42 + n)))
+sort = {"0": False, "1": True}.get(sys.argv[4]) if len(sys.argv) > 4 else None
+env = FactoryVecEnv("PauseIKToggleEnv", num_envs=n, num_arms=arms, seeds=list(range(42, 42 + n)), sort_envs=sort)
 env.reset()
 a = torch.ones((n, arms), dtype=torch.int32, device="cuda")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
